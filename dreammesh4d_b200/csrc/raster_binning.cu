@@ -1,0 +1,244 @@
+// Tile binning without a global sort and without a host read-back.
+//
+// The replaced rasterizer (un-vendored diff-gaussian-rasterization; bound by the reference at
+// custom/threestudio-dreammesh4d/renderer/diff_sugar_rasterizer_temporal.py:169-178) does
+// InclusiveSum(tiles_touched) -> D2H num_rendered -> duplicateWithKeys -> one global 64-bit
+// radix sort -> identifyTileRanges (SURVEY.md Appendix A.2 "binning").  Here:
+//   1. preprocess already counted instances per (view, tile) with atomics,
+//   2. scan_tiles_kernel: exclusive prefix sum over the (view, tile) counts -> tile ranges directly,
+//   3. scatter_kernel: every (view, Gaussian) drops (depth bits << 32 | id) into its tiles' segments,
+//   4. sort_pack_kernel: one CTA per (view, tile) sorts its segment on the full 64-bit key in shared
+//      memory (bitonic network; chunked with global merge steps for segments > 4096) and writes the
+//      depth-sorted instance stream of packed records that the render kernels pull with TMA bulk copies.
+// Order = ascending (tile, depth bits, Gaussian id) — exactly the order of upstream's stable radix
+// sort fed in ascending-id emission order, independent of atomics ordering.
+#include "raster_internal.cuh"
+
+namespace {
+
+constexpr int SCAN_THREADS = 1024;
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(RasterLayout L) {
+    __shared__ unsigned int warp_sums[SCAN_THREADS / 32];
+    __shared__ unsigned int carry_s;
+    const int n = L.n_views * L.tiles;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int beg = min(n, tid * per), end = min(n, beg + per);
+    unsigned int local = 0;
+    for (int i = beg; i < end; ++i) local += L.tile_count[i];
+    // block-wide exclusive scan of `local`
+    unsigned int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned int w = warp_sums[lane];
+        unsigned int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        warp_sums[lane] = wi - w;   // exclusive
+        if (lane == 31) carry_s = wi;
+    }
+    __syncthreads();
+    unsigned int run = warp_sums[wid] + (incl - local);
+    for (int i = beg; i < end; ++i) {
+        L.tile_offset[i] = run;
+        run += L.tile_count[i];
+        L.tile_cursor[i] = 0u;
+    }
+    if (tid == 0) {
+        const unsigned int total = carry_s;
+        L.tile_offset[n] = total;
+        L.hdr->total = total;
+        L.hdr->overflow = ((long long)total > L.capacity) ? 1u : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(DM4D_BLOCK) scatter_kernel(RasterLayout L) {
+    if (L.hdr->overflow) return;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)L.n_views * L.P) return;
+    const unsigned int rect = L.g_rect[idx];
+    if (rect == 0u) return;
+    const int v = (int)(idx / L.P);
+    const unsigned int g = (unsigned int)(idx - (long long)v * L.P);
+    const int minx = rect & 0xff, miny = (rect >> 8) & 0xff, maxx = (rect >> 16) & 0xff, maxy = rect >> 24;
+    const float depth = L.g_rec[(size_t)idx * L.rec + 6];
+    const unsigned long long key = ((unsigned long long)__float_as_uint(depth) << 32) | g;
+    const size_t tbase = (size_t)v * L.tiles;
+    for (int y = miny; y < maxy; ++y)
+        for (int x = minx; x < maxx; ++x) {
+            const size_t t = tbase + (size_t)y * L.gx + x;
+            const unsigned int slot = atomicAdd(&L.tile_cursor[t], 1u);
+            L.keys[L.tile_offset[t] + slot] = key;
+        }
+}
+
+// ---- per-tile sort ------------------------------------------------------------------------------
+constexpr int SORT_CHUNK = 4096;   // keys held in shared memory (32 KB)
+constexpr unsigned long long KEY_INF = 0xffffffffffffffffull;
+
+// Single-direction bitonic network on `n` real keys padded virtually with +inf up to `npow2`:
+// every compare-exchange puts the smaller key at the lower index, so the virtual +inf entries
+// (indices >= n) never move and can simply be skipped.
+__device__ __forceinline__ void cmpx(unsigned long long* k, int i, int j) {
+    const unsigned long long a = k[i], b = k[j];
+    if (a > b) { k[i] = b; k[j] = a; }
+}
+
+// All network steps whose span stays inside one SORT_CHUNK-aligned chunk held in shared memory.
+// kbeg..kend: merge sizes to run (powers of two); for merge size k > SORT_CHUNK only the
+// half-cleaner steps with stride < SORT_CHUNK are executed here.
+__device__ void smem_network(unsigned long long* sk, int cn /* pow2 <= SORT_CHUNK */, int kbeg, int kend) {
+    for (int k = kbeg; k <= kend; k <<= 1) {
+        int jstart;
+        if (k <= cn) {
+            // flip step: i <-> i ^ (k - 1) within blocks of size k
+            for (int t = threadIdx.x; t < cn / 2; t += blockDim.x) {
+                const int blk = t / (k / 2), off = t % (k / 2);
+                const int i = blk * k + off, j = blk * k + (k - 1 - off);
+                cmpx(sk, i, j);
+            }
+            __syncthreads();
+            jstart = k >> 2;
+        } else {
+            jstart = cn >> 1;
+        }
+        for (int j = jstart; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < cn / 2; t += blockDim.x) {
+                const int i = ((t / j) * 2 * j) + (t % j);
+                cmpx(sk, i, i + j);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DM4D_BLOCK) sort_pack_kernel(RasterLayout L) {
+    __shared__ unsigned long long sk[SORT_CHUNK];
+    if (L.hdr->overflow) return;
+    const int tile = blockIdx.x;                 // global (view, tile) index
+    const unsigned int beg = L.tile_offset[tile];
+    const int n = (int)(L.tile_offset[tile + 1] - beg);
+    if (n == 0) return;
+    const int v = tile / L.tiles;
+    unsigned long long* gk = L.keys + beg;
+    int npow2 = 2;
+    while (npow2 < n) npow2 <<= 1;
+
+    const float4* grec = reinterpret_cast<const float4*>(L.g_rec + (size_t)v * L.P * L.rec);
+    float4* srec = reinterpret_cast<float4*>(L.stream + (size_t)beg * L.rec);
+    const int r4 = L.rec / 4;
+
+    if (npow2 <= SORT_CHUNK) {
+        for (int i = threadIdx.x; i < npow2; i += blockDim.x) sk[i] = i < n ? gk[i] : KEY_INF;
+        __syncthreads();
+        smem_network(sk, npow2, 2, npow2);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned int id = (unsigned int)(sk[i] & 0xffffffffull);
+            const float4* src = grec + (size_t)id * r4;
+            float4* dst = srec + (size_t)i * r4;
+            for (int q = 0; q < r4; ++q) dst[q] = src[q];
+        }
+        return;
+    }
+
+    // Large segment: sort SORT_CHUNK-sized chunks in shared memory, then merge with global
+    // compare-exchange steps for strides >= SORT_CHUNK and shared-memory steps below.
+    const int nchunks = npow2 / SORT_CHUNK;
+    for (int c = 0; c < nchunks; ++c) {
+        const int base = c * SORT_CHUNK;
+        if (base >= n) break;
+        for (int i = threadIdx.x; i < SORT_CHUNK; i += blockDim.x) sk[i] = base + i < n ? gk[base + i] : KEY_INF;
+        __syncthreads();
+        smem_network(sk, SORT_CHUNK, 2, SORT_CHUNK);
+        for (int i = threadIdx.x; i < SORT_CHUNK; i += blockDim.x)
+            if (base + i < n) gk[base + i] = sk[i];
+        __syncthreads();
+    }
+    for (int k = 2 * SORT_CHUNK; k <= npow2; k <<= 1) {
+        // flip step (span up to k) in global memory
+        for (int t = threadIdx.x; t < npow2 / 2; t += blockDim.x) {
+            const int blk = t / (k / 2), off = t % (k / 2);
+            const int i = blk * k + off, j = blk * k + (k - 1 - off);
+            if (j < n) cmpx(gk, i, j);
+        }
+        __syncthreads();
+        for (int j = k >> 2; j >= SORT_CHUNK; j >>= 1) {
+            for (int t = threadIdx.x; t < npow2 / 2; t += blockDim.x) {
+                const int i = ((t / j) * 2 * j) + (t % j);
+                if (i + j < n) cmpx(gk, i, i + j);
+            }
+            __syncthreads();
+        }
+        for (int c = 0; c < nchunks; ++c) {
+            const int base = c * SORT_CHUNK;
+            if (base >= n) break;
+            for (int i = threadIdx.x; i < SORT_CHUNK; i += blockDim.x) sk[i] = base + i < n ? gk[base + i] : KEY_INF;
+            __syncthreads();
+            smem_network(sk, SORT_CHUNK, k, k);
+            for (int i = threadIdx.x; i < SORT_CHUNK; i += blockDim.x)
+                if (base + i < n) gk[base + i] = sk[i];
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned int id = (unsigned int)(gk[i] & 0xffffffffull);
+        const float4* src = grec + (size_t)id * r4;
+        float4* dst = srec + (size_t)i * r4;
+        for (int q = 0; q < r4; ++q) dst[q] = src[q];
+    }
+}
+
+__global__ void export_state_kernel(RasterLayout L, int view, unsigned int* ranges, unsigned int* point_list,
+                                    long long cap, unsigned int* n_contrib) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int vbeg = L.tile_offset[(size_t)view * L.tiles];
+    const unsigned int vend = L.tile_offset[(size_t)(view + 1) * L.tiles];
+    if (ranges && i < L.tiles) {
+        const unsigned int b = L.tile_offset[(size_t)view * L.tiles + i], e = L.tile_offset[(size_t)view * L.tiles + i + 1];
+        // empty tiles read (0,0) in the replaced rasterizer (zero-initialised ranges)
+        ranges[2 * i] = b == e ? 0u : b - vbeg;
+        ranges[2 * i + 1] = b == e ? 0u : e - vbeg;
+    }
+    if (point_list && i < (long long)(vend - vbeg) && i < cap)
+        point_list[i] = __float_as_uint(L.stream[(size_t)(vbeg + i) * L.rec + 7]);
+    if (n_contrib && i < (long long)L.H * L.W) n_contrib[i] = L.n_contrib[(size_t)view * L.H * L.W + i];
+}
+
+}  // namespace
+
+int launch_scan(const RasterLayout& L, cudaStream_t s) {
+    scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(L);
+    DM4D_CUDA_CHECK(cudaGetLastError());
+    return DM4D_OK;
+}
+
+int launch_scatter_sort_pack(const RasterLayout& L, cudaStream_t s) {
+    const long long n = (long long)L.n_views * L.P;
+    if (n == 0) return DM4D_OK;
+    scatter_kernel<<<(unsigned)((n + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(L);
+    DM4D_CUDA_CHECK(cudaGetLastError());
+    sort_pack_kernel<<<(unsigned)(L.n_views * L.tiles), DM4D_BLOCK, 0, s>>>(L);
+    DM4D_CUDA_CHECK(cudaGetLastError());
+    return DM4D_OK;
+}
+
+int launch_export_state(const RasterLayout& L, int view, unsigned int* ranges, unsigned int* point_list,
+                        long long cap, unsigned int* n_contrib, cudaStream_t s) {
+    long long n = L.tiles;
+    if ((long long)L.H * L.W > n) n = (long long)L.H * L.W;
+    if (point_list && L.capacity > n) n = L.capacity;
+    if (n == 0) return DM4D_OK;
+    export_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(L, view, ranges, point_list, cap, n_contrib);
+    DM4D_CUDA_CHECK(cudaGetLastError());
+    return DM4D_OK;
+}

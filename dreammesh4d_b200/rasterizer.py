@@ -1,0 +1,281 @@
+"""Host side of the rasterizer: autograd binding over the C ABI plus the drop-in
+``diff_gaussian_rasterization`` surface.
+
+Mirrors the Python API of the un-vendored ``diff-gaussian-rasterization`` (ashawkey fork) that
+the reference imports at
+custom/threestudio-dreammesh4d/renderer/diff_sugar_rasterizer_temporal.py:8-11 and calls at
+:129-144 (settings) and :169-178 / :202-211 (4-tuple return ``color, radii, depth, alpha``);
+surface restated in SURVEY.md Appendix A.1.  PyTorch is used for device memory, streams and
+autograd plumbing only; all arithmetic runs in libdm4d.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import DM4D_VIEW_STRIDE, RasterDesc, check, ptr
+
+
+# --------------------------------------------------------------------------------------------
+# view parameter blocks
+# --------------------------------------------------------------------------------------------
+def make_view_params(viewmatrix: torch.Tensor, projmatrix: torch.Tensor, campos: torch.Tensor, tanfovx, tanfovy,
+                     bg: torch.Tensor, scale_modifier: float = 1.0,
+                     set_index: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Packs per-view camera parameters into the [B, 48] fp32 block of include/dm4d.h.
+
+    ``viewmatrix`` / ``projmatrix`` are the transposed (row-vector) [B,4,4] matrices produced by
+    threestudio/utils/ops.py:398-413.  Everything stays on the device (no host sync).
+    """
+    dev = viewmatrix.device
+    B = viewmatrix.shape[0]
+    vp = torch.zeros(B, DM4D_VIEW_STRIDE, dtype=torch.float32, device=dev)
+    vp[:, 0:16] = viewmatrix.reshape(B, 16)
+    vp[:, 16:32] = projmatrix.reshape(B, 16)
+    vp[:, 32:35] = campos.reshape(B, 3)
+    vp[:, _lib.VIEW_TANFOVX] = torch.as_tensor(tanfovx, dtype=torch.float32, device=dev)
+    vp[:, _lib.VIEW_TANFOVY] = torch.as_tensor(tanfovy, dtype=torch.float32, device=dev)
+    vp[:, _lib.VIEW_SCALE_MOD] = float(scale_modifier)
+    if set_index is not None:
+        vp[:, _lib.VIEW_SET] = set_index.to(device=dev, dtype=torch.float32)
+    bg = bg.to(device=dev, dtype=torch.float32)
+    C = bg.shape[-1]
+    vp[:, _lib.VIEW_BG:_lib.VIEW_BG + C] = bg.reshape(-1, C)
+    return vp
+
+
+# --------------------------------------------------------------------------------------------
+# autograd binding
+# --------------------------------------------------------------------------------------------
+def _prep(t: torch.Tensor, k: int, name: str):
+    """Returns (contiguous fp32 tensor, set stride in floats, n_sets)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    t = t.contiguous()
+    if t.dim() == 2:
+        if t.shape[1] != k:
+            raise ValueError(f"{name} must be [P,{k}] or [S,P,{k}], got {tuple(t.shape)}")
+        return t, 0, 1
+    if t.dim() == 3 and t.shape[2] == k:
+        return t, t.shape[1] * k, t.shape[0]
+    raise ValueError(f"{name} must be [P,{k}] or [S,P,{k}], got {tuple(t.shape)}")
+
+
+class RasterState:
+    """Caller-owned scratch of one batch (kept alive for the backward)."""
+
+    def __init__(self, desc: RasterDesc, keep: list, capacity: int):
+        self.desc, self.keep, self.capacity = desc, keep, capacity
+
+    def status(self) -> tuple[int, bool]:
+        """(num_rendered, overflow) — synchronises the current stream."""
+        n = ctypes.c_int64(0)
+        o = ctypes.c_int32(0)
+        check(_lib.lib().dm4d_raster_status(ctypes.byref(self.desc), ctypes.byref(n), ctypes.byref(o),
+                                            torch.cuda.current_stream().cuda_stream), "dm4d_raster_status")
+        return int(n.value), bool(o.value)
+
+    def export_view(self, view: int):
+        """Integer binning state of one view (ranges [T,2], point_list [R_v], n_contrib [H,W])."""
+        d = self.desc
+        dev = self.keep[0].device
+        gx, gy = (d.W + 15) // 16, (d.H + 15) // 16
+        ranges = torch.zeros(gx * gy, 2, dtype=torch.int32, device=dev)
+        pl = torch.zeros(max(self.capacity, 1), dtype=torch.int32, device=dev)
+        nc = torch.zeros(d.H, d.W, dtype=torch.int32, device=dev)
+        check(_lib.lib().dm4d_raster_export_state(ctypes.byref(d), view, ptr(ranges), ptr(pl), pl.numel(), ptr(nc),
+                                                  torch.cuda.current_stream().cuda_stream), "dm4d_raster_export_state")
+        r_view = int(ranges[:, 1].max().item()) if ranges.numel() else 0
+        return ranges, pl[:r_view], nc
+
+
+class _RasterizeBatch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, opacities, scales, rotations, colors, colors2, view_params, H, W,
+                capacity, distinct_sets, state_out):
+        l = _lib.lib()
+        dev = means3D.device
+        if dev.type != "cuda":
+            raise _lib.Dm4dError("dreammesh4d_b200 rasterizer needs CUDA tensors (there is no CPU path)")
+        channels = 3 if colors2 is None else 6
+        m, ms, s0 = _prep(means3D, 3, "means3D")
+        sc, ss, s1 = _prep(scales, 3, "scales")
+        ro, rs, s2 = _prep(rotations, 4, "rotations")
+        op, os_, s3 = _prep(opacities.reshape(*opacities.shape[:-1], 1) if opacities.dim() >= 2 else opacities.reshape(-1, 1),
+                            1, "opacities")
+        co, cs, s4 = _prep(colors, 3, "colors_precomp")
+        c2, c2s, s5 = (None, 0, 1) if colors2 is None else _prep(colors2, 3, "colors2")
+        P = m.shape[-2]
+        for t, nm in ((sc, "scales"), (ro, "rotations"), (op, "opacities"), (co, "colors")):
+            if t.shape[-2] != P:
+                raise ValueError(f"{nm} has {t.shape[-2]} rows, means3D has {P}")
+        n_sets = max(s0, s1, s2, s3, s4, s5)
+        for s in (s0, s1, s2, s3, s4, s5):
+            if s not in (1, n_sets):
+                raise ValueError("attribute set counts disagree")
+        vp = view_params.contiguous().float()
+        B = vp.shape[0]
+        stream = torch.cuda.current_stream().cuda_stream
+
+        d = RasterDesc()
+        d.P, d.H, d.W, d.n_views, d.n_sets, d.channels = P, int(H), int(W), B, n_sets, channels
+        d.flags = _lib.RASTER_VIEWS_DISTINCT_SETS if (distinct_sets and n_sets == B) else 0
+        d.means3D, d.means3D_stride = ptr(m), ms
+        d.scales, d.scales_stride = ptr(sc), ss
+        d.rotations, d.rotations_stride = ptr(ro), rs
+        d.opacities, d.opacities_stride = ptr(op), os_
+        d.colors, d.colors_stride = ptr(co), cs
+        d.colors2, d.colors2_stride = ptr(c2), c2s
+        d.view_params = ptr(vp)
+
+        def sizes(cap):
+            g, b, i, w = (ctypes.c_uint64(0) for _ in range(4))
+            check(l.dm4d_raster_workspace_bytes(P, int(H), int(W), B, channels, int(cap), ctypes.byref(g),
+                                                ctypes.byref(b), ctypes.byref(i), ctypes.byref(w)),
+                  "dm4d_raster_workspace_bytes")
+            return g.value, b.value, i.value, w.value
+
+        u8 = dict(dtype=torch.uint8, device=dev)
+        radii = torch.empty(B, P, dtype=torch.int32, device=dev)
+        color = torch.empty(B, channels, H, W, dtype=torch.float32, device=dev)
+        depth = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+        alpha = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+
+        if capacity is None:
+            # exact sizing with one host read-back of num_rendered, like the replaced rasterizer:
+            # plan into a capacity-0 workspace to learn R, then run the forward at capacity R
+            gb, bb, ib, wb = sizes(0)
+            geom, img, bin0 = torch.empty(gb, **u8), torch.empty(ib, **u8), torch.empty(bb, **u8)
+            d.geom, d.geom_bytes, d.img, d.img_bytes = ptr(geom), gb, ptr(img), ib
+            d.bin, d.bin_bytes, d.bin_capacity = ptr(bin0), bb, 0
+            n = ctypes.c_int64(0)
+            check(l.dm4d_raster_plan(ctypes.byref(d), ptr(radii), ctypes.byref(n), stream), "dm4d_raster_plan")
+            capacity = int(n.value)
+            _, bb, _, _ = sizes(capacity)
+            bin_ = torch.empty(bb, **u8)
+            d.bin, d.bin_bytes, d.bin_capacity = ptr(bin_), bb, capacity
+            check(l.dm4d_raster_forward(ctypes.byref(d), ptr(color), ptr(depth), ptr(alpha), ptr(radii), stream),
+                  "dm4d_raster_forward")
+        else:
+            capacity = int(capacity)
+            gb, bb, ib, wb = sizes(capacity)
+            geom, bin_, img = torch.empty(gb, **u8), torch.empty(bb, **u8), torch.empty(ib, **u8)
+            d.geom, d.geom_bytes, d.img, d.img_bytes = ptr(geom), gb, ptr(img), ib
+            d.bin, d.bin_bytes, d.bin_capacity = ptr(bin_), bb, capacity
+            check(l.dm4d_raster_forward(ctypes.byref(d), ptr(color), ptr(depth), ptr(alpha), ptr(radii), stream),
+                  "dm4d_raster_forward")
+
+        state = RasterState(d, [m, sc, ro, op, co, c2, vp, geom, bin_, img, alpha], capacity)
+        ctx.state = state
+        ctx.shapes = (means3D.shape, scales.shape, rotations.shape, opacities.shape, colors.shape,
+                      None if colors2 is None else colors2.shape)
+        ctx.has_means2D = means2D is not None
+        ctx.mark_non_differentiable(radii)
+        if state_out is not None:
+            state_out.append(state)
+        return color, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, g_color, g_radii, g_depth, g_alpha):
+        l = _lib.lib()
+        st: RasterState = ctx.state
+        d = st.desc
+        m, sc, ro, op, co, c2, vp, geom, bin_, img, alpha = st.keep
+        dev = m.device
+        stream = torch.cuda.current_stream().cuda_stream
+        _, _, _, wb = (ctypes.c_uint64(0) for _ in range(4))
+        g_, b_, i_ = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+        check(l.dm4d_raster_workspace_bytes(d.P, d.H, d.W, d.n_views, d.channels, d.bin_capacity, ctypes.byref(g_),
+                                            ctypes.byref(b_), ctypes.byref(i_), ctypes.byref(wb)),
+              "dm4d_raster_workspace_bytes")
+        bwd = torch.empty(wb.value, dtype=torch.uint8, device=dev)
+        d.bwd, d.bwd_bytes = ptr(bwd), wb.value
+
+        gC = g_color.contiguous().float()
+        gD = None if g_depth is None else g_depth.contiguous().float()
+        gA = None if g_alpha is None else g_alpha.contiguous().float()
+        need = ctx.needs_input_grad
+        f32 = dict(dtype=torch.float32, device=dev)
+        d_means3D = torch.empty_like(m) if need[0] else None
+        d_means2D = torch.empty(d.n_views, d.P, 3, **f32) if (ctx.has_means2D and need[1]) else None
+        d_opac = torch.empty_like(op) if need[2] else None
+        d_scales = torch.empty_like(sc) if need[3] else None
+        d_rots = torch.empty_like(ro) if need[4] else None
+        d_colors = torch.empty_like(co) if need[5] else None
+        d_colors2 = torch.empty_like(c2) if (c2 is not None and need[6]) else None
+        check(l.dm4d_raster_backward(ctypes.byref(d), ptr(alpha), ptr(gC), ptr(gD), ptr(gA), ptr(d_means3D),
+                                     ptr(d_means2D), ptr(d_colors), ptr(d_colors2), ptr(d_opac), ptr(d_scales),
+                                     ptr(d_rots), stream), "dm4d_raster_backward")
+        sh = ctx.shapes
+        rs = lambda t, s: None if t is None else t.reshape(s)
+        return (rs(d_means3D, sh[0]), d_means2D, rs(d_opac, sh[3]), rs(d_scales, sh[1]), rs(d_rots, sh[2]),
+                rs(d_colors, sh[4]), None if d_colors2 is None else rs(d_colors2, sh[5]),
+                None, None, None, None, None, None)
+
+
+def rasterize_batch(means3D, opacities, scales, rotations, colors, view_params, H, W, colors2=None, means2D=None,
+                    capacity: Optional[int] = None, distinct_sets: bool = False, state_out: Optional[list] = None):
+    """Rasterizes a batch of views in one launch sequence.
+
+    Attributes are ``[P,k]`` (shared by all views) or ``[S,P,k]`` (one set per timestamp; each view picks
+    its set through ``view_params[:, 38]``).  ``means2D`` ([B,P,3], zeros) only serves as the holder of
+    the screen-space mean gradient, as in the reference (``viewspace_points``,
+    diff_sugar_rasterizer_temporal.py:108-113).  ``capacity=None`` sizes the binning workspace exactly
+    with one host read-back (the replaced rasterizer's behaviour); an integer keeps the call fully
+    asynchronous (check ``state.status()`` for overflow).
+    Returns ``color [B,C,H,W], radii [B,P] int32, depth [B,1,H,W], alpha [B,1,H,W]``.
+    """
+    return _RasterizeBatch.apply(means3D, means2D, opacities, scales, rotations, colors, colors2, view_params,
+                                 int(H), int(W), capacity, distinct_sets, state_out)
+
+
+# --------------------------------------------------------------------------------------------
+# drop-in diff_gaussian_rasterization surface
+# --------------------------------------------------------------------------------------------
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+class GaussianRasterizer(nn.Module):
+    """Same constructor/forward signature and 4-tuple return as the replaced module."""
+
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+                (scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        if cov3D_precomp is not None:
+            raise NotImplementedError("cov3D_precomp is not on the DreamMesh4D hot path "
+                                      "(the plugin always passes scales/rotations; DESIGN.md §7)")
+        if shs is not None:
+            raise NotImplementedError("SH evaluation inside the rasterizer is not on the DreamMesh4D hot path "
+                                      "(both systems pass colors_precomp; DESIGN.md §7)")
+        vp = make_view_params(rs.viewmatrix.reshape(1, 4, 4), rs.projmatrix.reshape(1, 4, 4),
+                              rs.campos.reshape(1, 3), rs.tanfovx, rs.tanfovy, rs.bg.reshape(1, -1)[:, :3],
+                              rs.scale_modifier)
+        m2d = None if means2D is None else means2D.reshape(1, -1, 3)
+        color, radii, depth, alpha = rasterize_batch(means3D, opacities, scales, rotations, colors_precomp, vp,
+                                                     rs.image_height, rs.image_width, means2D=m2d)
+        return color[0], radii[0], depth[0], alpha[0]

@@ -1,0 +1,183 @@
+/*
+ * dm4d.h — C ABI of libdm4d.so: the B200 (sm_100a) hot path of DreamMesh4D's dynamic stage.
+ *
+ * Plain pointers and sizes only; every data pointer is a DEVICE pointer unless its name ends
+ * in `_host`; `stream` is a cudaStream_t passed as void*.  The caller owns all memory
+ * (inputs, outputs and the scratch workspaces, sized by the *_workspace_bytes queries), the
+ * library owns none — the same ownership rule as the interface it replaces, where the
+ * rasterizer's scratch is resize_()d caller-side torch tensors.
+ * Every entry point returns 0 on success or a negative DM4D_E* code and never throws;
+ * dm4d_last_error() gives the message (thread-local).
+ *
+ * Reference interfaces replaced (paths under /root/reference/):
+ *   dm4d_raster_*  <- diff_gaussian_rasterization._C.rasterize_gaussians /
+ *                     rasterize_gaussians_backward (un-vendored dependency, README.md:35),
+ *                     as bound by GaussianRasterizer.forward at
+ *                     custom/threestudio-dreammesh4d/renderer/diff_sugar_rasterizer_temporal.py:144,169-178,202-211
+ *                     and .../diff_sugar_rasterizer_normal.py:132,161-195
+ *   dm4d_skin_*    <- DynamicSuGaRModel._get_timed_vertex_attributes_from_dg
+ *                     (custom/threestudio-dreammesh4d/geometry/dynamic_sugar.py:487-613),
+ *                     get_timed_gs_attributes (:657-706), _get_gs_xyz_from_vertex (:726-743),
+ *                     fuse_rotations (:877-889), get_timed_gs_normals (:357-364)
+ *   dm4d_sugar_rest_frames <- SuGaRModel.quaternions / get_gs_normals
+ *                     (custom/threestudio-dreammesh4d/geometry/sugar.py:490-526)
+ */
+#ifndef DM4D_H
+#define DM4D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM4D_OK 0
+#define DM4D_EINVAL (-1)   /* bad argument (shape, null pointer, unsupported option) */
+#define DM4D_ECUDA (-2)    /* a CUDA runtime call failed */
+#define DM4D_ENOSPC (-3)   /* a caller-provided workspace is too small */
+
+#define DM4D_TILE 16            /* tile edge in pixels (BLOCK_X = BLOCK_Y of the replaced rasterizer) */
+#define DM4D_MAX_CHANNELS 6     /* 3 (one pass) or 6 (RGB + normal pass fused, binning shared) */
+
+/* Per-view parameter block: DM4D_VIEW_STRIDE floats per view, device memory.
+ *   [ 0..15] viewmatrix   — world_view_transform, TRANSPOSED (row-vector) layout exactly as
+ *                           the plugin passes it (threestudio/utils/ops.py:400-402)
+ *   [16..31] projmatrix   — full_proj_transform, same layout (ops.py:408-410)
+ *   [32..34] campos       — camera_center (ops.py:411); used by the SH path only
+ *   [35] tanfovx [36] tanfovy [37] scale_modifier
+ *   [38] set index (integer stored as float): which attribute set this view renders
+ *   [39] reserved
+ *   [40..45] bg colour, `channels` entries                                           */
+#define DM4D_VIEW_STRIDE 48
+#define DM4D_VIEW_TANFOVX 35
+#define DM4D_VIEW_TANFOVY 36
+#define DM4D_VIEW_SCALE_MOD 37
+#define DM4D_VIEW_SET 38
+#define DM4D_VIEW_BG 40
+
+/* desc.flags: the caller promises n_sets == n_views and that the view -> set map is a bijection, so
+ * per-set gradients can be stored instead of accumulated with atomics. */
+#define DM4D_RASTER_VIEWS_DISTINCT_SETS 1
+
+/* A batch of views rasterized in one launch sequence.  Gaussian attributes are organised in
+ * "sets" (one per distinct timestamp in the dynamic stage, one in the static stage); each
+ * attribute has its own set stride in floats, 0 meaning "shared by every set"
+ * (opacity / colour / scale are time-invariant in the dynamic stage:
+ * dynamic_sugar.py:720-723).  All arrays are contiguous fp32, row-major. */
+typedef struct dm4d_raster_desc {
+    int32_t P;                 /* Gaussians per set */
+    int32_t H, W;              /* image size (pixels) */
+    int32_t n_views;
+    int32_t n_sets;
+    int32_t channels;          /* 3 or 6 */
+    int32_t flags;             /* DM4D_RASTER_* bits */
+    int32_t reserved1;
+    const float* means3D;   int64_t means3D_stride;     /* [., P, 3] */
+    const float* scales;    int64_t scales_stride;      /* [., P, 3] */
+    const float* rotations; int64_t rotations_stride;   /* [., P, 4] wxyz, NOT re-normalised */
+    const float* opacities; int64_t opacities_stride;   /* [., P, 1] */
+    const float* colors;    int64_t colors_stride;      /* [., P, 3] colors_precomp */
+    const float* colors2;   int64_t colors2_stride;     /* [., P, 3] channels 3..5 (NULL if channels==3) */
+    const float* view_params;                           /* [n_views, DM4D_VIEW_STRIDE] */
+    void* geom; uint64_t geom_bytes;                    /* per-(view,Gaussian) projected state */
+    void* bin;  uint64_t bin_bytes;                     /* tile counts/offsets, keys, sorted instance stream */
+    void* img;  uint64_t img_bytes;                     /* per-pixel n_contrib */
+    void* bwd;  uint64_t bwd_bytes;                     /* backward accumulators (may be NULL for forward) */
+    int64_t bin_capacity;                               /* instance capacity the bin workspace was sized for */
+} dm4d_raster_desc;
+
+/* Workspace sizes for a batch. `bin_capacity` = max number of (Gaussian, tile) instances. */
+int dm4d_raster_workspace_bytes(int32_t P, int32_t H, int32_t W, int32_t n_views, int32_t channels,
+                                int64_t bin_capacity, uint64_t* geom_bytes, uint64_t* bin_bytes,
+                                uint64_t* img_bytes, uint64_t* bwd_bytes);
+
+/* Phase A of the forward: project every (view, Gaussian), write radii [n_views, P] (int32), count
+ * instances per tile and prefix-sum them.  If `num_rendered_host` is non-NULL the stream is
+ * synchronised and the total instance count R is returned (the replaced rasterizer always does
+ * this read-back); pass NULL to stay asynchronous and size `bin` from a capacity bound instead. */
+int dm4d_raster_plan(const dm4d_raster_desc* d, int32_t* radii, int64_t* num_rendered_host, void* stream);
+
+/* Phase B: scatter instances to their tiles, depth-sort every tile, pack the sorted instance
+ * stream and alpha-composite.  Outputs: color [n_views, channels, H, W], depth [n_views,1,H,W],
+ * alpha [n_views,1,H,W].  If R exceeded bin_capacity nothing is rendered and the device-side
+ * overflow flag is set (see dm4d_raster_status). */
+int dm4d_raster_render(const dm4d_raster_desc* d, float* out_color, float* out_depth, float* out_alpha,
+                       void* stream);
+
+/* plan (asynchronous) + render. */
+int dm4d_raster_forward(const dm4d_raster_desc* d, float* out_color, float* out_depth, float* out_alpha,
+                        int32_t* radii, void* stream);
+
+/* Synchronises `stream` and reports the instance count and overflow flag of the last plan. */
+int dm4d_raster_status(const dm4d_raster_desc* d, int64_t* num_rendered_host, int32_t* overflow_host,
+                       void* stream);
+
+/* Backward of dm4d_raster_forward for the same desc/workspaces; `out_alpha` is the forward's alpha
+ * output (the replaced rasterizer saves it the same way).  dL_ddepth / dL_dalpha may be
+ * NULL (zero).  Gradient outputs have the shape of the matching input ([n_sets or 1, P, k]) and
+ * are fully overwritten (summed over the views that used each set entry);
+ * dL_dmeans2D is [n_views, P, 3] (z = 0, NDC-scaled as in the replaced rasterizer).
+ * Any output pointer may be NULL to skip it. */
+int dm4d_raster_backward(const dm4d_raster_desc* d, const float* out_alpha, const float* dL_dcolor,
+                         const float* dL_ddepth, const float* dL_dalpha, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcolors,
+                         float* dL_dcolors2, float* dL_dopacities, float* dL_dscales, float* dL_drotations,
+                         void* stream);
+
+/* Test/inspection helper: copies the integer binning state of one view to device arrays:
+ * ranges [tiles, 2] (uint32, relative to the view's first instance), point_list [R_view] (uint32
+ * Gaussian ids in sorted order), n_contrib [H, W] (uint32). Any pointer may be NULL. */
+int dm4d_raster_export_state(const dm4d_raster_desc* d, int32_t view, uint32_t* ranges, uint32_t* point_list,
+                             int64_t point_list_capacity, uint32_t* n_contrib, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sparse-control-point skinning + per-face surface-bound Gaussian update (fused).
+ * n_t timestamps are deformed in one launch sequence.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dm4d_skin_desc {
+    int32_t n_t;               /* timestamps in this batch */
+    int32_t V, F, M, K;        /* vertices, faces, control nodes, neighbours per vertex */
+    int32_t g;                 /* Gaussians per face (1, 3, 4 or 6); P = F * g */
+    int32_t method;            /* 0 = lbs, 1 = dqs, 2 = hybrid (dynamic_sugar.py:72) */
+    int32_t reserved0;
+    const float* rest_verts;   /* [V, 3]  SuGaRModel._points */
+    const int32_t* faces;      /* [F, 3]  _surface_mesh_faces (int32) */
+    const int32_t* nbr_idx;    /* [V, K]  _xyz_neighbor_node_idx (int32) */
+    const float* nbr_w;        /* [V, K]  _xyz_neighbor_nodes_weights (row-normalised) */
+    const float* bary;         /* [g, 3]  surface_triangle_bary_coords */
+    const float* rest_quat;    /* [P, 4]  wxyz rest-pose quaternion (SuGaRModel.quaternions) */
+    const float* node_trans;   /* [n_t, M, 3] */
+    const float* node_rot;     /* [n_t, M, 4] xyzw, unit */
+    const float* node_scale;   /* [n_t, M, 9] row-major 3x3 (I + strain) */
+    const float* node_opacity; /* [n_t, M]    sigmoid'ed lbs weight */
+} dm4d_skin_desc;
+
+/* Outputs: verts [n_t,V,3], vert_rot [n_t,V,4] xyzw, means3D [n_t,P,3], rotations [n_t,P,4] wxyz
+ * (normalised), normals [n_t,P,3] (deformed unit face normal repeated g times; may be NULL). */
+int dm4d_skin_forward(const dm4d_skin_desc* d, float* verts, float* vert_rot, float* means3D,
+                      float* rotations, float* normals, void* stream);
+
+/* Backward: incoming dL_dmeans3D [n_t,P,3], dL_drotations [n_t,P,4], dL_dnormals [n_t,P,3] (any may
+ * be NULL), plus optional direct gradients on the deformed vertices dL_dverts_in [n_t,V,3] and vertex
+ * rotations dL_dvert_rot_in [n_t,V,4] (ARAP / mesh regularisers).  `verts`/`vert_rot` are the forward
+ * outputs.  Scratch: dverts [n_t,V,3] and dvert_rot [n_t,V,4] (caller-owned, overwritten).
+ * Outputs (overwritten): dL_dnode_trans [n_t,M,3], dL_dnode_rot [n_t,M,4], dL_dnode_scale [n_t,M,9],
+ * dL_dnode_opacity [n_t,M].  Exact Euclidean gradients of the forward formulas. */
+int dm4d_skin_backward(const dm4d_skin_desc* d, const float* verts, const float* vert_rot,
+                       const float* dL_dmeans3D, const float* dL_drotations, const float* dL_dnormals,
+                       const float* dL_dverts_in, const float* dL_dvert_rot_in, float* dverts, float* dvert_rot,
+                       float* dL_dnode_trans, float* dL_dnode_rot, float* dL_dnode_scale,
+                       float* dL_dnode_opacity, void* stream);
+
+/* Rest-pose frames of the surface-bound Gaussians: quaternions [P,4] wxyz (normalised) and unit
+ * face normals repeated g times [P,3] (either may be NULL). complex_rot is SuGaRModel._quaternions [P,2]. */
+int dm4d_sugar_rest_frames(const float* verts, const int32_t* faces, const float* complex_rot, int32_t V,
+                           int32_t F, int32_t g, float* quaternions, float* normals, void* stream);
+
+const char* dm4d_last_error(void);
+int dm4d_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DM4D_H */

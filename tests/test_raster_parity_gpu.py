@@ -1,0 +1,196 @@
+"""GPU parity: libdm4d.so rasterizer (through the C ABI / drop-in module) vs the CPU oracle.
+
+Tolerances are the north-star's: 1e-4 relative L-inf on colour/depth/alpha, 1e-3 on gradients,
+bit-exact integer state (radii, tile ranges, sorted instance ids, n_contrib).  Pixels whose
+compositing decisions sit within the oracle's ambiguity margin of a hard threshold
+(alpha < 1/255, T < 1e-4, power > 0) are excluded and counted.
+"""
+import numpy as np
+import pytest
+import torch
+
+from dreammesh4d_b200 import rasterizer as R
+from dreammesh4d_b200 import synthetic
+from oracle.raster_oracle import RasterOracle
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+MAX_AMBIG_FRACTION = 2e-3
+
+
+def run_oracle(P, H, W, means, scales, rots, opac, cols, V, PV, tanx, tany, bg, C=3):
+    o = RasterOracle(P, H, W, C, "f32")
+    o.forward(means.numpy(), scales.numpy(), rots.numpy(), opac.numpy(), cols.numpy(), V.numpy(), PV.numpy(),
+              float(tanx), float(tany), np.asarray(bg, dtype=np.float32))
+    return o
+
+
+def check_view(o: RasterOracle, color, radii, depth, alpha, state, view, check_state=True):
+    amb = o.ambiguous
+    ok = ~amb
+    assert amb.mean() <= MAX_AMBIG_FRACTION, f"too many ambiguous pixels: {amb.mean()}"
+    np.testing.assert_array_equal(radii.cpu().numpy(), o.radii)
+    if check_state:
+        ranges, pl, nc = state.export_view(view)
+        np.testing.assert_array_equal(ranges.cpu().numpy().astype(np.uint32), o.ranges)
+        ids, _ = o.point_list()
+        np.testing.assert_array_equal(pl.cpu().numpy().astype(np.uint32), ids)
+        np.testing.assert_array_equal(nc.cpu().numpy().astype(np.uint32)[ok], o.n_contrib[ok])
+    for name, got, ref in (("color", color, o.color), ("depth", depth, o.depth), ("alpha", alpha, o.alpha)):
+        got = got.detach().cpu().numpy()
+        m = np.broadcast_to(ok, ref.shape)
+        err = np.abs(got - ref)[m].max() / max(np.abs(ref).max(), 1e-30)
+        assert err <= Hh.TOL_IMAGE, f"{name}: rel Linf {err}"
+    return ok
+
+
+@pytest.mark.parametrize("P,H,W,seed", [(3000, 100, 130, 0), (20000, 256, 256, 1), (64, 48, 64, 2)])
+def test_dropin_single_view_forward_backward(P, H, W, seed):
+    means, scales, rots, opac, cols = Hh.random_scene(P, seed)
+    V, PV, campos, tanx, tany = Hh.cameras(1, seed=seed + 10)
+    bg = torch.tensor([1.0, 1.0, 1.0])
+    o = run_oracle(P, H, W, means, scales, rots, opac, cols, V[0], PV[0], tanx[0], tany[0], bg)
+
+    t = lambda x: x.to(DEV).requires_grad_(True)
+    tm, ts, tr, to_, tc = t(means), t(scales), t(rots), t(opac), t(cols)
+    m2d = torch.zeros(P, 3, device=DEV, requires_grad=True)
+    settings = R.GaussianRasterizationSettings(H, W, float(tanx[0]), float(tany[0]), bg.to(DEV), 1.0, V[0].to(DEV),
+                                               PV[0].to(DEV), 0, campos[0].to(DEV), False, False)
+    states = []
+    vp = R.make_view_params(V[:1].to(DEV), PV[:1].to(DEV), campos[:1].to(DEV), tanx[:1], tany[:1], bg[None].to(DEV))
+    color, radii, depth, alpha = R.rasterize_batch(tm, to_, ts, tr, tc, vp, H, W, means2D=m2d[None], state_out=states)
+    ok = check_view(o, color[0], radii[0], depth[0], alpha[0], states[0], 0)
+
+    # drop-in module gives the same numbers
+    c2, r2, d2, a2 = R.GaussianRasterizer(settings)(means3D=tm, means2D=m2d, opacities=to_, colors_precomp=tc,
+                                                     scales=ts, rotations=tr)
+    assert torch.equal(c2, color[0]) and torch.equal(r2, radii[0]) and torch.equal(d2, depth[0]) and torch.equal(a2, alpha[0])
+
+    g = torch.Generator().manual_seed(seed)
+    gC = torch.randn(3, H, W, generator=g) * torch.from_numpy(ok)[None]
+    gD = torch.randn(1, H, W, generator=g) * torch.from_numpy(ok)[None]
+    gA = torch.randn(1, H, W, generator=g) * torch.from_numpy(ok)[None]
+    (color[0] * gC.to(DEV)).sum().add((depth[0] * gD.to(DEV)).sum()).add((alpha[0] * gA.to(DEV)).sum()).backward()
+    ref = o.backward(gC.numpy(), gD.numpy(), gA.numpy())
+    for name, tt in (("means3D", tm), ("means2D", m2d), ("colors", tc), ("opacities", to_), ("scales", ts),
+                     ("rotations", tr)):
+        err = Hh.rel_linf(tt.grad.cpu().numpy(), ref[name])
+        assert err <= Hh.TOL_GRAD, f"grad {name}: rel Linf {err}"
+
+
+def test_sugar_sphere_c1_static():
+    """BASELINE config 1 geometry: 10k-face sphere, 30k bound Gaussians, 256x256, 1 view."""
+    scene = synthetic.make_sugar_scene(10_000, g=3)
+    means, scales, rots, opac, cols, normals = Hh.sugar_gaussians(scene)
+    P, H, W = means.shape[0], 256, 256
+    V, PV, campos, tanx, tany = Hh.cameras(1, seed=5)
+    bg = torch.tensor([1.0, 1.0, 1.0])
+    o = run_oracle(P, H, W, means, scales, rots, opac, cols, V[0], PV[0], tanx[0], tany[0], bg)
+    vp = R.make_view_params(V.to(DEV), PV.to(DEV), campos.to(DEV), tanx, tany, bg[None].to(DEV))
+    states = []
+    t = lambda x: x.to(DEV).requires_grad_(True)
+    tm, ts, tr, to_, tc = t(means), t(scales), t(rots), t(opac), t(cols)
+    color, radii, depth, alpha = R.rasterize_batch(tm, to_, ts, tr, tc, vp, H, W, state_out=states)
+    ok = check_view(o, color[0], radii[0], depth[0], alpha[0], states[0], 0)
+    assert (alpha > 0.5).float().mean() > 0.2     # the sphere is actually in view
+    gC = torch.randn(3, H, W) * torch.from_numpy(ok)[None]
+    (color[0] * gC.to(DEV)).sum().backward()
+    ref = o.backward(gC.numpy())
+    for name, tt in (("means3D", tm), ("colors", tc), ("opacities", to_), ("scales", ts), ("rotations", tr)):
+        err = Hh.rel_linf(tt.grad.cpu().numpy(), ref[name])
+        assert err <= Hh.TOL_GRAD, f"grad {name}: rel Linf {err}"
+
+
+def test_batched_views_sets_and_fused_six_channels():
+    """4 views over 2 attribute sets; the 6-channel fused pass equals two 3-channel passes and the oracle."""
+    P, H, W, B, S = 5000, 128, 128, 4, 2
+    means, scales, rots, opac, cols = Hh.random_scene(P, 3)
+    means2 = means + 0.05 * torch.randn(P, 3, generator=torch.Generator().manual_seed(9))
+    nrm = torch.nn.functional.normalize(torch.randn(S, P, 3, generator=torch.Generator().manual_seed(4)), dim=-1)
+    V, PV, campos, tanx, tany = Hh.cameras(B, seed=7)
+    bg = torch.tensor([1.0, 1.0, 1.0, 1.0, 1.0, 1.0])
+    set_idx = torch.tensor([0, 1, 1, 0])
+    vp6 = R.make_view_params(V.to(DEV), PV.to(DEV), campos.to(DEV), tanx, tany, bg[None].expand(B, -1).to(DEV),
+                             set_index=set_idx)
+    M = torch.stack([means, means2]).to(DEV).requires_grad_(True)
+    N = nrm.to(DEV).requires_grad_(True)
+    t = lambda x: x.to(DEV).requires_grad_(True)
+    ts, tr, to_, tc = t(scales), t(rots), t(opac), t(cols)
+    states = []
+    col6, radii, depth, alpha = R.rasterize_batch(M, to_, ts, tr, tc, vp6, H, W, colors2=N, state_out=states)
+    gC = torch.randn(B, 6, H, W, generator=torch.Generator().manual_seed(5))
+    oks, refs = [], []
+    for v in range(B):
+        s = int(set_idx[v])
+        m = [means, means2][s]
+        feat = torch.cat([cols, nrm[s]], dim=1)
+        o = run_oracle(P, H, W, m, scales, rots, opac, feat, V[v], PV[v], tanx[v], tany[v], bg, C=6)
+        ok = check_view(o, col6[v], radii[v], depth[v], alpha[v], states[0], v)
+        gC[v] *= torch.from_numpy(ok)[None]
+        refs.append(o.backward(gC[v].numpy()))
+        oks.append(ok)
+    (col6 * gC.to(DEV)).sum().backward()
+    # expected: per-set sums over the views that used the set; shared attributes sum over all views
+    exp_means = np.zeros((S, P, 3)); exp_n = np.zeros((S, P, 3))
+    exp = {k: 0.0 for k in ("scales", "rotations", "opacities")}
+    exp_cols = 0.0
+    for v in range(B):
+        s = int(set_idx[v])
+        exp_means[s] += refs[v]["means3D"]
+        exp_n[s] += refs[v]["colors"][:, 3:]
+        exp_cols = exp_cols + refs[v]["colors"][:, :3]
+        for k in exp:
+            exp[k] = exp[k] + refs[v][k]
+    assert Hh.rel_linf(M.grad.cpu().numpy(), exp_means) <= Hh.TOL_GRAD
+    assert Hh.rel_linf(N.grad.cpu().numpy(), exp_n) <= Hh.TOL_GRAD
+    assert Hh.rel_linf(tc.grad.cpu().numpy(), exp_cols) <= Hh.TOL_GRAD
+    assert Hh.rel_linf(ts.grad.cpu().numpy(), exp["scales"]) <= Hh.TOL_GRAD
+    assert Hh.rel_linf(tr.grad.cpu().numpy(), exp["rotations"]) <= Hh.TOL_GRAD
+    assert Hh.rel_linf(to_.grad.cpu().numpy(), exp["opacities"]) <= Hh.TOL_GRAD
+
+    # two 3-channel passes (the reference's call pattern) give bit-identical images
+    vp3 = vp6.clone()
+    c_rgb, _, d3, a3 = R.rasterize_batch(M.detach(), to_.detach(), ts.detach(), tr.detach(), tc.detach(), vp3, H, W)
+    c_nrm, _, _, _ = R.rasterize_batch(M.detach(), to_.detach(), ts.detach(), tr.detach(), N.detach(), vp3, H, W)
+    assert torch.equal(c_rgb, col6[:, :3]) and torch.equal(c_nrm, col6[:, 3:])
+    assert torch.equal(d3, depth) and torch.equal(a3, alpha)
+
+
+def test_capacity_mode_and_overflow_flag():
+    P, H, W = 4000, 96, 96
+    means, scales, rots, opac, cols = Hh.random_scene(P, 11)
+    V, PV, campos, tanx, tany = Hh.cameras(2, seed=3)
+    bg = torch.ones(2, 3)
+    vp = R.make_view_params(V.to(DEV), PV.to(DEV), campos.to(DEV), tanx, tany, bg.to(DEV))
+    args = [x.to(DEV) for x in (means, opac, scales, rots, cols)]
+    st = []
+    ref = R.rasterize_batch(*args, vp, H, W, state_out=st)
+    n, over = st[0].status()
+    assert n > 0 and not over
+    st2 = []
+    got = R.rasterize_batch(*args, vp, H, W, capacity=n + 1000, state_out=st2)
+    assert st2[0].status() == (n, False)
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
+    st3 = []
+    R.rasterize_batch(*args, vp, H, W, capacity=max(n // 2, 1), state_out=st3)
+    assert st3[0].status() == (n, True)
+
+
+def test_empty_and_fully_culled_inputs():
+    H, W = 64, 64
+    V, PV, campos, tanx, tany = Hh.cameras(1, seed=1)
+    bg = torch.tensor([[0.25, 0.5, 0.75]])
+    vp = R.make_view_params(V.to(DEV), PV.to(DEV), campos.to(DEV), tanx, tany, bg.to(DEV))
+    # every Gaussian behind the camera
+    P = 100
+    means, scales, rots, opac, cols = Hh.random_scene(P, 1)
+    means = means + campos[0] * 2.0
+    color, radii, depth, alpha = R.rasterize_batch(*[x.to(DEV) for x in (means, opac, scales, rots, cols)], vp, H, W)
+    assert int(radii.abs().sum()) == 0 and float(alpha.abs().max()) == 0.0
+    assert torch.allclose(color[0], bg.to(DEV)[0][:, None, None].expand(3, H, W))
+    # P = 0
+    z = lambda k: torch.zeros(0, k, device=DEV)
+    color, radii, depth, alpha = R.rasterize_batch(z(3), z(1), z(3), z(4), z(3), vp, H, W)
+    assert radii.shape == (1, 0) and torch.allclose(color[0], bg.to(DEV)[0][:, None, None].expand(3, H, W))
