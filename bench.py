@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — rasterize fwd+bwd throughput of the DreamMesh4D dynamic-stage hot path on B200.
+
+Metric (BASELINE.json): rasterize fwd+bwd Gaussians/s @512x512, 8 views
+    value = P * n_views * n_gpus / t(fwd+bwd)          [Gaussians/s, whole job]
+Workload at every N: BASELINE config C3 geometry — 100k-face sphere, 300k surface-bound Gaussians,
+8 views per rank per step, each view at its own timestamp (8 attribute sets), 512x512, white bg,
+one 3-channel pass with colour+depth+alpha gradients.  Weak scaling: every rank
+renders its own 8 cameras; for N>1 the gradients of the time-invariant attributes are summed with
+one NCCL all-reduce per step (the path's only exchange step).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+N>1 is launched by torchrun (one process per GPU).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np
+import torch
+
+WORKLOAD = "C3: 100k-face sphere, 300k surface-bound Gaussians, 8 views x 8 timestamps per rank, 512x512, 1 pass (3ch) fwd+bwd"
+N_FACES, G_PER_FACE, H, W, VIEWS = 100_000, 3, 512, 512, 8
+M_NODES, K_NBR = 1000, 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--small", action="store_true", help="tiny workload for a functional check (not a bench number)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# workload (synthetic)
+# ------------------------------------------------------------------------------------------------
+def build_workload(rank: int, small: bool):
+    """Returns CPU tensors: per-timestamp Gaussian sets + cameras for this rank."""
+    from dreammesh4d_b200 import synthetic
+    from dreammesh4d_b200.camera import get_cam_info_gaussian
+    from dreammesh4d_b200 import hostref
+
+    n_faces = 2_000 if small else N_FACES
+    scene = synthetic.make_sugar_scene(n_faces, g=G_PER_FACE)
+    graph = synthetic.make_deform_graph(scene.verts, 64 if small else M_NODES, K_NBR, seed=0)
+    node = synthetic.random_node_attrs(VIEWS, graph.node_xyz.shape[0], seed=1)
+    gs = hostref.deform_gaussians_cpu(scene, graph, *node)      # setup only (untimed): per-timestamp sets
+    c2w, fovy = synthetic.random_orbit_cameras(VIEWS, seed=2 + rank)
+    V, PV, campos, tanx, tany = get_cam_info_gaussian(c2w, fovy, fovy)
+    return scene, gs, (V, PV, campos, tanx, tany)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU with NVML during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# per-kernel ALGORITHMIC bytes per launch; R = instances in the launch, n = views*P, px = views*H*W
+def algorithmic_bytes(kernel: str, n: int, R: int, px: int, tiles: int) -> float:
+    return {
+        "preprocess_kernel": 56.0 * n + 56.0 * n + 4.0 * R,          # read attributes; write record+radius+rect; count atomics
+        "scan_tiles_kernel": 12.0 * tiles,
+        "scatter_kernel": 8.0 * n + 8.0 * R + 4.0 * R,              # rect+depth; key write; cursor atomics
+        "sort_pack_kernel": 8.0 * R + 48.0 * R + 48.0 * R,           # keys; record gather; stream write
+        "render_forward_kernel": 48.0 * R + 24.0 * px,               # stream; colour(12)+depth+alpha+n_contrib
+        "render_backward_kernel": 48.0 * R + 28.0 * px + 48.0 * n,   # stream; dL(20)+n_contrib+alpha; accumulator rows
+        "preprocess_backward_kernel": 56.0 * n + 48.0 * n + 40.0 * n,
+    }.get(kernel, 0.0)
+
+
+def run_ours(args):
+    from dreammesh4d_b200 import _lib
+    from dreammesh4d_b200 import rasterizer as R
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torchrun (python -m torch.distributed.run --nproc-per-node N bench.py --gpus N)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+
+    scene, gs, cams = build_workload(rank, args.small)
+    means, rots, normals = gs["means3D"], gs["rotations"], gs["normals"]      # [8,P,3], [8,P,4]
+    scales, opac, cols = gs["scales"], gs["opacities"], gs["colors"]         # shared [P,k]
+    P = means.shape[1]
+    V, PV, campos, tanx, tany = cams
+    bg = torch.ones(VIEWS, 3)
+    set_idx = torch.arange(VIEWS)
+
+    # ---- device-resident copies for `value` ----
+    d = lambda t: t.to(dev).contiguous()
+    vp = R.make_view_params(d(V), d(PV), d(campos), tanx, tany, d(bg), set_index=set_idx)
+    g = torch.Generator().manual_seed(1234 + rank)
+    gC_h = torch.randn(VIEWS, 3, H, W, generator=g).pin_memory()
+    gD_h = torch.randn(VIEWS, 1, H, W, generator=g).mul_(0.1).pin_memory()
+    gA_h = torch.randn(VIEWS, 1, H, W, generator=g).pin_memory()
+    host_in = {k: v.contiguous().pin_memory() for k, v in
+               dict(means=means, rots=rots, scales=scales, opac=opac, cols=cols).items()}
+    dev_in = {k: d(v).requires_grad_(True) for k, v in host_in.items()}
+    gC, gD, gA = d(gC_h), d(gD_h), d(gA_h)
+
+    # capacity: one synchronous run tells R; afterwards the path is free of host syncs
+    st = []
+    with torch.no_grad():
+        R.rasterize_batch(dev_in["means"], dev_in["opac"], dev_in["scales"], dev_in["rots"], dev_in["cols"], vp, H, W,
+                          state_out=st)
+    n_rendered, _ = st[0].status()
+    capacity = int(n_rendered * 1.25) + 4096
+    del st
+
+    def step(inp):
+        out_state = []
+        color, radii, depth, alpha = R.rasterize_batch(inp["means"], inp["opac"], inp["scales"], inp["rots"],
+                                                       inp["cols"], vp, H, W, capacity=capacity, distinct_sets=True,
+                                                       state_out=out_state)
+        torch.autograd.backward([color, depth, alpha], [gC, gD, gA])
+        grads = {k: inp[k].grad for k in inp}
+        if dist is not None:   # exchange step: time-invariant attribute gradients (scale / opacity / colour)
+            flat = torch.cat([grads["scales"].reshape(-1), grads["opac"].reshape(-1), grads["cols"].reshape(-1)])
+            dist.all_reduce(flat)
+        for k in inp:
+            inp[k].grad = None
+        return color, depth, alpha, grads, out_state[0]
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(dev_in)
+    barrier()
+
+    # ---- timed: K steps, CUDA events per step on the launch stream, L2 flushed between steps ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _lib.profile_enable(True)
+    _lib.profile_collect()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    last_state = None
+    for i in range(args.steps):
+        flush_buf.zero_()
+        ev[i][0].record()
+        *_, last_state = step(dev_in)
+        ev[i][1].record()
+    barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+    n_r, overflow = last_state.status()
+    if overflow:
+        raise SystemExit("bin capacity overflow during the timed region — result invalid")
+
+    # ---- e2e: same step through the public API with HOST (pinned) buffers, copies inside the timed region ----
+    e2e_in = {k: torch.empty_like(v, device=dev).requires_grad_(True) for k, v in host_in.items()}
+    out_host = {k: torch.empty_like(v).pin_memory() for k, v in host_in.items()}
+    img_host = torch.empty(VIEWS, 5, H, W).pin_memory()
+    h2d = sum(v.numel() * 4 for v in host_in.values()) + (gC_h.numel() + gD_h.numel() + gA_h.numel()) * 4
+    d2h = sum(v.numel() * 4 for v in out_host.values()) + img_host.numel() * 4
+
+    def e2e_step():
+        with torch.no_grad():
+            for k in e2e_in:
+                e2e_in[k].copy_(host_in[k], non_blocking=True)
+            gC.copy_(gC_h, non_blocking=True); gD.copy_(gD_h, non_blocking=True); gA.copy_(gA_h, non_blocking=True)
+        color, depth, alpha, grads, _ = step(e2e_in)
+        with torch.no_grad():
+            for k in out_host:
+                out_host[k].copy_(grads[k], non_blocking=True)
+            img_host[:, 0:3].copy_(color, non_blocking=True)
+            img_host[:, 3:4].copy_(depth, non_blocking=True)
+            img_host[:, 4:5].copy_(alpha, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e_steps = max(3, min(args.steps, 10))
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e_steps)]
+    for i in range(e_steps):
+        flush_buf.zero_()
+        ev2[i][0].record()
+        e2e_step()
+        ev2[i][1].record()
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    clocks = sampler.result()
+
+    # ---- max over ranks ----
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    e2e_ms_per_step = e2e_ms / e_steps
+    value = P * VIEWS * world / (ms_per_step * 1e-3)
+    e2e_value = P * VIEWS * world / (e2e_ms_per_step * 1e-3)
+
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        kern = {k: {"ms_per_launch": ms / max(n, 1), "launches": n, "share": ms / max(sum(m for m, _ in prof.values()), 1e-9)}
+                for k, (ms, n) in prof.items()}
+        dom = max(prof, key=lambda k: prof[k][0]) if prof else None
+        roof = None
+        if dom:
+            tiles = VIEWS * ((H + 15) // 16) * ((W + 15) // 16)
+            ab = algorithmic_bytes(dom, VIEWS * P, n_r, VIEWS * H * W, tiles)
+            dur = prof[dom][0] / prof[dom][1] * 1e-3
+            ach = ab / dur / 1e9
+            traffic = None
+            tf = ROOT / "profiles" / "traffic.json"
+            if tf.exists():
+                try:
+                    traffic = json.loads(tf.read_text()).get(dom)
+                except Exception:
+                    traffic = None
+            roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": traffic, "algorithmic_bytes": ab,
+                    "launch_ms": round(dur * 1e3, 4), "peak_source": peak_src}
+        cpu = cpu_baseline_sample(host_in, cams, P, views=1 if not args.small else 1)
+        out = {
+            "metric": "rasterize fwd+bwd Gaussians/s @512x512, 8 views/GPU", "value": value, "unit": "Gaussians/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD if not args.small else "SMALL functional check (not a bench number)",
+                       "P": P, "views_per_gpu": VIEWS, "H": H, "W": W, "num_rendered": n_r,
+                       "l2": "flushed between steps (256 MiB write, outside the per-step events)",
+                       "timing": "CUDA events per step on the launch stream, summed over K steps, max over ranks",
+                       "exchange": "none" if world == 1 else "NCCL all-reduce of time-invariant attribute grads (8.4 MB) per step"},
+            "e2e": {"value": e2e_value, "unit": "Gaussians/s", "ms_per_step": e2e_ms_per_step,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps},
+            "gpu_launches": int(sum(n for _, n in prof.values())),
+            "kernels": kern, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+        }
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle legs
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline_sample(host_in, cams, P, views: int, reps: int = 1):
+    """Times the CPU oracle (oracle/raster_oracle.c, OpenMP on every host core) on `views` of the
+    same workload: forward + backward. Reported baseline, not the target."""
+    from oracle.raster_oracle import RasterOracle, cpu_threads
+    V, PV, campos, tanx, tany = cams
+    g = np.random.default_rng(0)
+    gC = g.standard_normal((3, H, W)).astype(np.float32)
+    gD = (0.1 * g.standard_normal((1, H, W))).astype(np.float32)
+    gA = g.standard_normal((1, H, W)).astype(np.float32)
+    o = RasterOracle(P, H, W, 3, "f32")
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(reps):
+        for v in range(views):
+            o.forward(host_in["means"][v].numpy(), host_in["scales"].numpy(), host_in["rots"][v].numpy(),
+                      host_in["opac"].numpy(), host_in["cols"].numpy(), V[v].numpy(), PV[v].numpy(), float(tanx[v]),
+                      float(tany[v]), np.ones(3, np.float32))
+            o.backward(gC, gD, gA)
+            done += 1
+    dt = time.perf_counter() - t0
+    return {"value": P * done / dt, "unit": "Gaussians/s", "cores": cpu_threads(), "kind": "port",
+            "sample": f"{done} view(s) of the same workload ({P} Gaussians, {H}x{W}), fwd+bwd, {dt:.2f} s",
+            "seconds": dt}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's rasterizer is CUDA-only and not obtainable here,
+    so this arm times the CPU oracle port on all host cores; each step = 1 view of the same workload."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return None
+    scene, gs, cams = build_workload(0, args.small)
+    host_in = dict(means=gs["means3D"], rots=gs["rotations"], scales=gs["scales"], opac=gs["opacities"], cols=gs["colors"])
+    P = host_in["means"].shape[1]
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline_sample(host_in, cams, P, views=1)
+    steps = max(1, min(args.steps, 8))
+    t0 = time.perf_counter()
+    vals = [cpu_baseline_sample(host_in, (cams[0][i % VIEWS:], cams[1][i % VIEWS:], cams[2][i % VIEWS:], cams[3][i % VIEWS:], cams[4][i % VIEWS:]),
+                                P, views=1) for i in range(steps)]
+    dt = time.perf_counter() - t0
+    value = P * steps / dt
+    from oracle.raster_oracle import cpu_threads
+    cpu = {"value": value, "unit": "Gaussians/s", "cores": cpu_threads(), "kind": "port",
+           "sample": f"each step = 1 view of the workload ({P} Gaussians, {H}x{W}) fwd+bwd on the CPU oracle; {steps} steps"}
+    return {"impl": "reference", "metric": "rasterize fwd+bwd Gaussians/s @512x512, 8 views/GPU", "value": value,
+            "unit": "Gaussians/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "P": P, "H": H, "W": W, "note": "bounded sample: 1 view per step"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": value, "unit": "Gaussians/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    args = parse()
+    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -60,9 +60,14 @@ SIGNATURES = {
     "dm4d_skin_forward": (ctypes.c_int, [POINTER(SkinDesc)] + [c_void_p] * 6),
     "dm4d_skin_backward": (ctypes.c_int, [POINTER(SkinDesc)] + [c_void_p] * 14),
     "dm4d_sugar_rest_frames": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "dm4d_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "dm4d_profile_collect": (ctypes.c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
+    "dm4d_kernel_name": (c_char_p, [ctypes.c_int]),
     "dm4d_last_error": (c_char_p, []),
     "dm4d_version": (ctypes.c_int, []),
 }
+
+K_COUNT = 12
 
 _lib = None
 
@@ -97,3 +102,15 @@ def check(rc: int, what: str) -> None:
 def ptr(t) -> int | None:
     """Device pointer of a torch tensor (or None)."""
     return None if t is None else t.data_ptr()
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().dm4d_profile_enable(1 if on else 0), "dm4d_profile_enable")
+
+
+def profile_collect() -> dict[str, tuple[float, int]]:
+    """{kernel name: (total ms, launches)} since the last collect (synchronises the recorded events)."""
+    ms = (ctypes.c_double * K_COUNT)()
+    n = (c_int64 * K_COUNT)()
+    check(lib().dm4d_profile_collect(ms, n), "dm4d_profile_collect")
+    return {lib().dm4d_kernel_name(i).decode(): (ms[i], n[i]) for i in range(K_COUNT) if n[i]}

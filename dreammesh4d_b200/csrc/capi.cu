@@ -2,6 +2,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <vector>
 #include "raster_internal.cuh"
 
 static thread_local char g_err[512] = "";
@@ -164,4 +166,53 @@ extern "C" int dm4d_raster_export_state(const dm4d_raster_desc* d, int32_t view,
     if (rc) return rc;
     if (view < 0 || view >= d->n_views) { dm4d_set_error("view out of range"); return DM4D_EINVAL; }
     return launch_export_state(L, view, ranges, point_list, point_list_capacity, n_contrib, (cudaStream_t)stream);
+}
+
+// ---- per-kernel event timing ---------------------------------------------------------------------
+namespace {
+struct Rec { int id; cudaEvent_t e0, e1; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<Rec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+const char* const kNames[DM4D_K_COUNT] = {
+    "preprocess_kernel", "scan_tiles_kernel", "scatter_kernel", "sort_pack_kernel", "render_forward_kernel",
+    "render_backward_kernel", "preprocess_backward_kernel", "skin_vertex_forward_kernel",
+    "skin_gaussian_forward_kernel", "skin_gaussian_backward_kernel", "skin_vertex_backward_kernel",
+    "sugar_rest_frames_kernel"};
+}  // namespace
+
+KernelTimer::KernelTimer(int id_, cudaStream_t s_) : id(id_), s(s_), on(g_prof_on), e0(nullptr) {
+    if (!on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    e0 = prof_event();
+    cudaEventRecord(e0, s);
+}
+KernelTimer::~KernelTimer() {
+    if (!on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t e1 = prof_event();
+    cudaEventRecord(e1, s);
+    g_prof_recs.push_back({id, e0, e1});
+}
+
+extern "C" int dm4d_profile_enable(int on) { g_prof_on = on != 0; return DM4D_OK; }
+extern "C" const char* dm4d_kernel_name(int id) { return (id >= 0 && id < DM4D_K_COUNT) ? kNames[id] : ""; }
+extern "C" int dm4d_profile_collect(double* ms_host, int64_t* launches_host) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof_recs) {
+        DM4D_CUDA_CHECK(cudaEventSynchronize(r.e1));
+        float ms = 0.f;
+        DM4D_CUDA_CHECK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        if (ms_host) ms_host[r.id] += ms;
+        if (launches_host) launches_host[r.id] += 1;
+        g_prof_pool.push_back(r.e0);
+        g_prof_pool.push_back(r.e1);
+    }
+    g_prof_recs.clear();
+    return DM4D_OK;
 }

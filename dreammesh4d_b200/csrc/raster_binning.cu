@@ -217,7 +217,7 @@ __global__ void export_state_kernel(RasterLayout L, int view, unsigned int* rang
 }  // namespace
 
 int launch_scan(const RasterLayout& L, cudaStream_t s) {
-    scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(L);
+    { KernelTimer kt(DM4D_K_SCAN, s); scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(L); }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }
@@ -225,9 +225,9 @@ int launch_scan(const RasterLayout& L, cudaStream_t s) {
 int launch_scatter_sort_pack(const RasterLayout& L, cudaStream_t s) {
     const long long n = (long long)L.n_views * L.P;
     if (n == 0) return DM4D_OK;
-    scatter_kernel<<<(unsigned)((n + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(L);
+    { KernelTimer kt(DM4D_K_SCATTER, s); scatter_kernel<<<(unsigned)((n + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(L); }
     DM4D_CUDA_CHECK(cudaGetLastError());
-    sort_pack_kernel<<<(unsigned)(L.n_views * L.tiles), DM4D_BLOCK, 0, s>>>(L);
+    { KernelTimer kt(DM4D_K_SORT_PACK, s); sort_pack_kernel<<<(unsigned)(L.n_views * L.tiles), DM4D_BLOCK, 0, s>>>(L); }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }

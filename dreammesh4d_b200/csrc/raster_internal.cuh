@@ -71,3 +71,10 @@ int launch_render_backward(const dm4d_raster_desc* d, const RasterLayout& L, con
                            const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, cudaStream_t s);
 int launch_export_state(const RasterLayout& L, int view, unsigned int* ranges, unsigned int* point_list,
                         long long cap, unsigned int* n_contrib, cudaStream_t s);
+
+// Optional per-kernel event timing (dm4d_profile_*). Usage: { KernelTimer t(DM4D_K_X, stream); kernel<<<...>>>(); }
+struct KernelTimer {
+    int id; cudaStream_t s; bool on; cudaEvent_t e0;
+    KernelTimer(int id_, cudaStream_t s_);
+    ~KernelTimer();
+};

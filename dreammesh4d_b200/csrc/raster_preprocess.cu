@@ -333,7 +333,7 @@ int launch_preprocess(const dm4d_raster_desc* d, const RasterLayout& L, int32_t*
     if (n == 0) return DM4D_OK;
     PreArgs a = make_args(d, L, radii);
     const unsigned blocks = (unsigned)((n + DM4D_BLOCK - 1) / DM4D_BLOCK);
-    preprocess_kernel<<<blocks, DM4D_BLOCK, 0, s>>>(a);
+    { KernelTimer kt(DM4D_K_PREPROCESS, s); preprocess_kernel<<<blocks, DM4D_BLOCK, 0, s>>>(a); }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }
@@ -368,7 +368,7 @@ int launch_preprocess_backward(const dm4d_raster_desc* d, const RasterLayout& L,
     b.dscales = dL_dscales;   b.dscales_atomic = mode(dL_dscales, d->scales_stride, P * 3);
     b.drots = dL_drotations;  b.drots_atomic = mode(dL_drotations, d->rotations_stride, P * 4);
     const unsigned blocks = (unsigned)((n + DM4D_BLOCK - 1) / DM4D_BLOCK);
-    preprocess_backward_kernel<<<blocks, DM4D_BLOCK, 0, s>>>(b);
+    { KernelTimer kt(DM4D_K_PREPROCESS_BWD, s); preprocess_backward_kernel<<<blocks, DM4D_BLOCK, 0, s>>>(b); }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }

@@ -358,8 +358,11 @@ int launch_fwd_t(const dm4d_raster_desc* d, const RasterLayout& L, float* out_co
         DM4D_CUDA_CHECK(cudaFuncSetAttribute(render_forward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    render_forward_kernel<C><<<(unsigned)(L.n_views * L.tiles), CHUNK, smem, s>>>(L, d->view_params, out_color,
-                                                                                  out_depth, out_alpha);
+    {
+        KernelTimer kt(DM4D_K_RENDER_FWD, s);
+        render_forward_kernel<C><<<(unsigned)(L.n_views * L.tiles), CHUNK, smem, s>>>(L, d->view_params, out_color,
+                                                                                      out_depth, out_alpha);
+    }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }
@@ -376,8 +379,11 @@ int launch_bwd_t(const dm4d_raster_desc* d, const RasterLayout& L, const float* 
         configured = true;
     }
     DM4D_CUDA_CHECK(cudaMemsetAsync(L.accum, 0, (size_t)L.n_views * L.P * L.acc * sizeof(float), s));
-    render_backward_kernel<C><<<(unsigned)(L.n_views * L.tiles), CHUNK, smem, s>>>(L, d->view_params, out_alpha,
-                                                                                   dL_dcolor, dL_ddepth, dL_dalpha);
+    {
+        KernelTimer kt(DM4D_K_RENDER_BWD, s);
+        render_backward_kernel<C><<<(unsigned)(L.n_views * L.tiles), CHUNK, smem, s>>>(L, d->view_params, out_alpha,
+                                                                                       dL_dcolor, dL_ddepth, dL_dalpha);
+    }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }

@@ -174,6 +174,19 @@ int dm4d_skin_backward(const dm4d_skin_desc* d, const float* verts, const float*
 int dm4d_sugar_rest_frames(const float* verts, const int32_t* faces, const float* complex_rot, int32_t V,
                            int32_t F, int32_t g, float* quaternions, float* normals, void* stream);
 
+/* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel launch).
+ * Kernel ids: see DM4D_K_* below.  dm4d_profile_collect synchronises the recorded events, ADDS the
+ * elapsed milliseconds / launch counts since the last collect into ms[DM4D_K_COUNT] /
+ * launches[DM4D_K_COUNT] (host arrays) and clears the record. */
+enum {
+    DM4D_K_PREPROCESS = 0, DM4D_K_SCAN, DM4D_K_SCATTER, DM4D_K_SORT_PACK, DM4D_K_RENDER_FWD,
+    DM4D_K_RENDER_BWD, DM4D_K_PREPROCESS_BWD, DM4D_K_SKIN_VERT_FWD, DM4D_K_SKIN_GAUSS_FWD,
+    DM4D_K_SKIN_GAUSS_BWD, DM4D_K_SKIN_VERT_BWD, DM4D_K_REST_FRAMES, DM4D_K_COUNT
+};
+int dm4d_profile_enable(int on);
+int dm4d_profile_collect(double* ms_host, int64_t* launches_host);
+const char* dm4d_kernel_name(int id);
+
 const char* dm4d_last_error(void);
 int dm4d_version(void);
 

@@ -1,0 +1,87 @@
+"""CPU: the oracles against the committed golden vectors (tests/golden/*.npz, produced by executing the
+reference's own skinning / SuGaR code — see tests/golden/make_skinning_golden.py) and against each other."""
+import types
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import skin_oracle as SO
+
+GOLD = Path(__file__).resolve().parent / "golden"
+TAGS = ["f64_g3_hybrid", "f32_g6_hybrid", "f64_g3_lbs", "f64_g3_dqs"]
+
+
+def load(tag):
+    z = np.load(GOLD / f"skinning_{tag}.npz")
+    t = {k: torch.from_numpy(z[k]) for k in z.files if k not in ("method",)}
+    t["method"] = str(z["method"])
+    return t
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_skinning_oracle_matches_reference_code(tag):
+    z = load(tag)
+    dtype = z["verts"].dtype
+    tol = 1e-12 if dtype == torch.float64 else 2e-5
+    g = int(z["g"])
+    scene = types.SimpleNamespace(verts=z["verts"], faces=z["faces"], bary=z["bary"], log_scales=z["log_scales"],
+                                  complex_rot=z["complex_rot"], densities=z["densities"], sh_dc=z["sh_dc"],
+                                  thickness=float(z["thickness"]), g=g)
+    graph = types.SimpleNamespace(nbr_idx=z["nbr_idx"], nbr_w=z["nbr_w"])
+    out = SO.deform_gaussians(scene, graph, z["node_trans"], z["node_rot"], z["node_scale"], z["node_opacity"],
+                              method=z["method"], dtype=dtype)
+
+    def close(a, b, name):
+        err = (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+        assert err <= tol, f"{name}: {err}"
+
+    close(out["verts"], z["out_vert_xyz"], "vertex xyz")
+    # quaternions are compared up to sign (q == -q)
+    def qclose(a, b, name):
+        s = torch.sign((a * b).sum(-1, keepdim=True))
+        close(a * s, b, name)
+    qclose(out["vert_rot"], z["out_vert_rot"], "vertex rotation")
+    close(out["means3D"], z["out_gs_xyz"], "gaussian xyz")
+    qclose(out["rotations"], z["out_gs_rot"], "gaussian rotation")
+    close(out["normals"], z["out_gs_normals"], "gaussian normals")
+    # static getters
+    close(SO.sugar_points(z["verts"], z["faces"], z["bary"]), z["out_static_xyz"], "static xyz")
+    close(out["scales"], z["out_static_scaling"], "static scaling")
+    qclose(out["rest_quat"], z["out_static_rot"], "static rotation")
+    close(out["opacities"], z["out_static_opacity"], "static opacity")
+    close(out["colors"], z["out_static_rgb"], "static rgb")
+    close(SO.faces_normals(z["verts"], z["faces"]).repeat_interleave(g, dim=0), z["out_static_normals"], "static normals")
+    # renderer-facing single-time call (t index 1)
+    close(out["means3D"][1], z["out_single_means"], "single means")
+    qclose(out["rotations"][1], z["out_single_rot"], "single rot")
+    close(out["scales"], z["out_single_scales"], "single scales")
+    close(out["opacities"], z["out_single_opacity"], "single opacity")
+    close(out["colors"], z["out_single_colors"], "single colors")
+
+
+def test_strain_tensor_to_matrix_golden():
+    z = np.load(GOLD / "strain.npz")
+    got = SO.strain_tensor_to_matrix(torch.from_numpy(z["strain"]))
+    np.testing.assert_allclose(got.numpy(), z["matrix"], rtol=0, atol=0)
+
+
+def test_identity_deformation_is_identity():
+    """Zero-init heads (deformation.py:507-512) => t=0, q=identity, S=I: skinning must be the identity map."""
+    from dreammesh4d_b200 import synthetic
+    scene = synthetic.make_sugar_scene(264, g=3)
+    graph = synthetic.make_deform_graph(scene.verts, 16, 4)
+    T, M = 2, 16
+    trans = torch.zeros(T, M, 3, dtype=torch.float64)
+    rot = torch.zeros(T, M, 4, dtype=torch.float64); rot[..., 3] = 1
+    scale = torch.eye(3, dtype=torch.float64).expand(T, M, 3, 3).clone()
+    opac = torch.full((T, M, 1), 0.5, dtype=torch.float64)
+    for method in ("lbs", "dqs", "hybrid"):
+        out = SO.deform_gaussians(scene, graph, trans, rot, scale, opac, method=method, dtype=torch.float64)
+        assert (out["verts"] - scene.verts.double()[None]).abs().max() < 1e-6
+        assert (out["vert_rot"] - rot[:, :1]).abs().max() < 1e-6
+        static = SO.sugar_points(scene.verts.double(), scene.faces, scene.bary.double())
+        assert (out["means3D"] - static[None]).abs().max() < 1e-6
+        s = torch.sign((out["rotations"] * out["rest_quat"][None]).sum(-1, keepdim=True))
+        assert (out["rotations"] * s - out["rest_quat"][None]).abs().max() < 1e-6
