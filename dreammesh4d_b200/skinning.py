@@ -1,0 +1,122 @@
+"""Host side of the fused skinning + surface-bound Gaussian update (autograd binding over the C ABI).
+
+Mirrors what DynamicSuGaRModel computes between the deformation network and the rasterizer:
+``_get_timed_vertex_attributes_from_dg`` -> ``get_timed_gs_attributes`` -> ``get_timed_gs_normals``
+(custom/threestudio-dreammesh4d/geometry/dynamic_sugar.py:487-613, 657-706, 357-364), for all
+timestamps of a step in one launch sequence.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import SkinDesc, check, ptr
+
+METHODS = {"lbs": 0, "dqs": 1, "hybrid": 2}
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+class _SkinFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, node_trans, node_rot, node_scale, node_opacity, rest_verts, faces, nbr_idx, nbr_w, bary,
+                rest_quat, method, want_normals):
+        l = _lib.lib()
+        dev = node_trans.device
+        if dev.type != "cuda":
+            raise _lib.Dm4dError("dreammesh4d_b200 skinning needs CUDA tensors (there is no CPU path)")
+        if faces.dtype != torch.int32 or nbr_idx.dtype != torch.int32:
+            raise TypeError("faces / nbr_idx must be int32 (convert once at setup)")
+        nt, ns, nr, no = _f32(node_trans), _f32(node_scale).reshape(*node_scale.shape[:2], 9), _f32(node_rot), \
+            _f32(node_opacity).reshape(node_opacity.shape[0], -1)
+        T, M = nt.shape[0], nt.shape[1]
+        V, F, K, g = rest_verts.shape[0], faces.shape[0], nbr_idx.shape[1], bary.shape[0]
+        P = F * g
+        d = SkinDesc()
+        d.n_t, d.V, d.F, d.M, d.K, d.g, d.method = T, V, F, M, K, g, METHODS[method]
+        keep = [_f32(rest_verts), faces.contiguous(), nbr_idx.contiguous(), _f32(nbr_w), _f32(bary).reshape(g, 3),
+                _f32(rest_quat), nt, nr, ns, no]
+        (d.rest_verts, d.faces, d.nbr_idx, d.nbr_w, d.bary, d.rest_quat, d.node_trans, d.node_rot, d.node_scale,
+         d.node_opacity) = [ptr(t) for t in keep]
+        f32 = dict(dtype=torch.float32, device=dev)
+        verts = torch.empty(T, V, 3, **f32)
+        vert_rot = torch.empty(T, V, 4, **f32)
+        means = torch.empty(T, P, 3, **f32)
+        rots = torch.empty(T, P, 4, **f32)
+        normals = torch.empty(T, P, 3, **f32) if want_normals else None
+        check(l.dm4d_skin_forward(ctypes.byref(d), ptr(verts), ptr(vert_rot), ptr(means), ptr(rots), ptr(normals),
+                                  torch.cuda.current_stream().cuda_stream), "dm4d_skin_forward")
+        ctx.desc, ctx.keep = d, keep + [verts, vert_rot]
+        ctx.shapes = (node_trans.shape, node_rot.shape, node_scale.shape, node_opacity.shape)
+        ctx.want_normals = want_normals
+        if not want_normals:
+            normals = torch.empty(0, **f32)
+            ctx.mark_non_differentiable(normals)
+        return means, rots, normals, verts, vert_rot
+
+    @staticmethod
+    def backward(ctx, g_means, g_rots, g_normals, g_verts, g_vert_rot):
+        l = _lib.lib()
+        d: SkinDesc = ctx.desc
+        verts, vert_rot = ctx.keep[-2], ctx.keep[-1]
+        dev = verts.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        c = lambda t: None if t is None else t.contiguous().float()
+        g_means, g_rots, g_verts, g_vert_rot = c(g_means), c(g_rots), c(g_verts), c(g_vert_rot)
+        g_normals = c(g_normals) if ctx.want_normals else None
+        T, V, M = d.n_t, d.V, d.M
+        dverts = torch.empty(T, V, 3, **f32)
+        dvrot = torch.empty(T, V, 4, **f32)
+        dn_t = torch.empty(T, M, 3, **f32)
+        dn_r = torch.empty(T, M, 4, **f32)
+        dn_s = torch.empty(T, M, 9, **f32)
+        dn_o = torch.empty(T, M, **f32)
+        check(l.dm4d_skin_backward(ctypes.byref(d), ptr(verts), ptr(vert_rot), ptr(g_means), ptr(g_rots),
+                                   ptr(g_normals), ptr(g_verts), ptr(g_vert_rot), ptr(dverts), ptr(dvrot), ptr(dn_t),
+                                   ptr(dn_r), ptr(dn_s), ptr(dn_o), torch.cuda.current_stream().cuda_stream),
+              "dm4d_skin_backward")
+        sh = ctx.shapes
+        return (dn_t.reshape(sh[0]), dn_r.reshape(sh[1]), dn_s.reshape(sh[2]), dn_o.reshape(sh[3]),
+                None, None, None, None, None, None, None, None)
+
+
+def skin_gaussians(node_trans, node_rot, node_scale, node_opacity, rest_verts, faces, nbr_idx, nbr_w, bary, rest_quat,
+                   method: str = "hybrid", want_normals: bool = True):
+    """Deforms the mesh with the control-node attributes of ``T`` timestamps and updates the bound Gaussians.
+
+    node_trans [T,M,3], node_rot [T,M,4] (xyzw, unit), node_scale [T,M,3,3], node_opacity [T,M,1] — the
+    outputs of ``get_timed_dg_attributes`` (dynamic_sugar.py:367-405).  Static inputs: rest_verts [V,3],
+    faces [F,3] int32, nbr_idx [V,K] int32, nbr_w [V,K], bary [g,3], rest_quat [P,4] wxyz.
+    Returns means3D [T,P,3], rotations [T,P,4] (wxyz, normalised), normals [T,P,3] (or empty),
+    verts [T,V,3], vert_rot [T,V,4] (xyzw).  Differentiable w.r.t. the four node tensors.
+    """
+    if method not in METHODS:
+        raise ValueError(f"skinning_method must be one of {list(METHODS)}")
+    return _SkinFunction.apply(node_trans, node_rot, node_scale, node_opacity, rest_verts, faces, nbr_idx, nbr_w,
+                               bary, rest_quat, method, want_normals)
+
+
+def sugar_rest_frames(verts: torch.Tensor, faces: torch.Tensor, complex_rot: Optional[torch.Tensor], g: int,
+                      want_quaternions: bool = True, want_normals: bool = True):
+    """Rest-pose quaternions [P,4] (wxyz) and per-Gaussian face normals [P,3] (sugar.py:490-526). No autograd
+    (the static parameters are frozen in the dynamic stage, dynamic_sugar.py:79-87)."""
+    l = _lib.lib()
+    dev = verts.device
+    if dev.type != "cuda":
+        raise _lib.Dm4dError("dreammesh4d_b200 needs CUDA tensors (there is no CPU path)")
+    v = _f32(verts)
+    f = faces.contiguous()
+    if f.dtype != torch.int32:
+        raise TypeError("faces must be int32")
+    c = None if complex_rot is None else _f32(complex_rot)
+    P = f.shape[0] * g
+    q = torch.empty(P, 4, dtype=torch.float32, device=dev) if want_quaternions else None
+    n = torch.empty(P, 3, dtype=torch.float32, device=dev) if want_normals else None
+    check(l.dm4d_sugar_rest_frames(ptr(v), ptr(f), ptr(c), v.shape[0], f.shape[0], g, ptr(q), ptr(n),
+                                   torch.cuda.current_stream().cuda_stream), "dm4d_sugar_rest_frames")
+    return q, n
