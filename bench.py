@@ -41,26 +41,48 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--small", action="store_true", help="tiny workload for a functional check (not a bench number)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------
 # workload (synthetic)
 # ------------------------------------------------------------------------------------------------
-def build_workload(rank: int, small: bool):
-    """Returns CPU tensors: per-timestamp Gaussian sets + cameras for this rank."""
+def build_scene(small: bool):
     from dreammesh4d_b200 import synthetic
-    from dreammesh4d_b200.camera import get_cam_info_gaussian
-    from dreammesh4d_b200 import hostref
-
     n_faces = 2_000 if small else N_FACES
     scene = synthetic.make_sugar_scene(n_faces, g=G_PER_FACE)
     graph = synthetic.make_deform_graph(scene.verts, 64 if small else M_NODES, K_NBR, seed=0)
     node = synthetic.random_node_attrs(VIEWS, graph.node_xyz.shape[0], seed=1)
-    gs = hostref.deform_gaussians_cpu(scene, graph, *node)      # setup only (untimed): per-timestamp sets
+    return scene, graph, node
+
+
+def build_cameras(rank: int):
+    from dreammesh4d_b200 import synthetic
+    from dreammesh4d_b200.camera import get_cam_info_gaussian
     c2w, fovy = synthetic.random_orbit_cameras(VIEWS, seed=2 + rank)
-    V, PV, campos, tanx, tany = get_cam_info_gaussian(c2w, fovy, fovy)
-    return scene, gs, (V, PV, campos, tanx, tany)
+    return get_cam_info_gaussian(c2w, fovy, fovy)
+
+
+def gaussian_sets_gpu(scene, graph, node, dev):
+    """Per-timestamp Gaussian sets produced by the product path (fused skinning kernels), on the GPU."""
+    from dreammesh4d_b200 import skinning, synthetic
+    d = lambda t: t.to(dev)
+    faces = d(scene.faces.int())
+    rest_q, _ = skinning.sugar_rest_frames(d(scene.verts), faces, d(scene.complex_rot), scene.g)
+    with torch.no_grad():
+        means, rots, normals, _, _ = skinning.skin_gaussians(*[d(t) for t in node], d(scene.verts), faces,
+                                                             d(graph.nbr_idx.int()), d(graph.nbr_w), d(scene.bary), rest_q)
+    scales = torch.cat([torch.full((scene.n_gaussians, 1), scene.thickness), scene.log_scales.exp()], dim=-1)
+    return {"means3D": means, "rotations": rots, "normals": normals, "scales": d(scales),
+            "opacities": d(torch.sigmoid(scene.densities)), "colors": d(scene.sh_dc[:, 0] * synthetic.C0 + 0.5)}
+
+
+def gaussian_sets_oracle(scene, graph, node):
+    """Same sets from the CPU oracle (used only by the CPU legs; never by the product path)."""
+    from oracle import skin_oracle
+    with torch.no_grad():
+        return skin_oracle.deform_gaussians(scene, graph, *node)
 
 
 class ClockSampler(threading.Thread):
@@ -132,7 +154,14 @@ def algorithmic_bytes(kernel: str, n: int, R: int, px: int, tiles: int) -> float
     }.get(kernel, 0.0)
 
 
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
+    import warnings
+    warnings.filterwarnings("ignore", message=".*AccumulateGrad node's stream.*")
+    log("importing")
     from dreammesh4d_b200 import _lib
     from dreammesh4d_b200 import rasterizer as R
 
@@ -150,7 +179,10 @@ def run_ours(args):
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
 
-    scene, gs, cams = build_workload(rank, args.small)
+    log("building workload")
+    scene, graph, node = build_scene(args.small)
+    cams = build_cameras(rank)
+    gs = {k: v.cpu() for k, v in gaussian_sets_gpu(scene, graph, node, dev).items()}
     means, rots, normals = gs["means3D"], gs["rotations"], gs["normals"]      # [8,P,3], [8,P,4]
     scales, opac, cols = gs["scales"], gs["opacities"], gs["colors"]         # shared [P,k]
     P = means.shape[1]
@@ -200,37 +232,67 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step(dev_in)
-    barrier()
+    import gc
+    gc.collect()
+    gc.freeze()          # keep the cyclic GC out of the timed regions
 
+    def make_runner(fn):
+        """Warm up `fn` and (unless --no-graph) capture it into a CUDA graph: the whole step — forward,
+        backward, exchange — becomes one launch, so host jitter cannot open gaps between kernels."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(args.warmup, 3)):
+                out = fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if args.no_graph:
+            return fn, out
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = fn()
+        return graph.replay, out
+
+    def timed(run, n):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        barrier()
+        for i in range(n):
+            flush_buf.zero_()
+            ev[i][0].record()
+            run()
+            ev[i][1].record()
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in ev)
+
+    log("warm-up + capture")
     # ---- timed: K steps, CUDA events per step on the launch stream, L2 flushed between steps ----
+    run_step, step_out = make_runner(lambda: step(dev_in))
     sampler = ClockSampler(local_rank)
     sampler.start()
-    _lib.profile_enable(True)
-    _lib.profile_collect()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    last_state = None
-    for i in range(args.steps):
-        flush_buf.zero_()
-        ev[i][0].record()
-        *_, last_state = step(dev_in)
-        ev[i][1].record()
-    barrier()
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    prof = _lib.profile_collect()
-    _lib.profile_enable(False)
-    n_r, overflow = last_state.status()
+    total_ms = timed(run_step, args.steps)
+    n_r, overflow = step_out[-1].status()
     if overflow:
         raise SystemExit("bin capacity overflow during the timed region — result invalid")
+
+    log(f"timed region done: {total_ms / args.steps:.3f} ms/step")
+    # ---- per-kernel device times (CUDA events around every launch inside libdm4d), same steps, eager ----
+    _lib.profile_enable(True)
+    _lib.profile_collect()
+    prof_steps = max(3, min(args.steps, 10))
+    for _ in range(prof_steps):
+        flush_buf.zero_()
+        step(dev_in)
+    torch.cuda.synchronize()
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+    launches_per_step = int(sum(n for _, n in prof.values())) // prof_steps
 
     # ---- e2e: same step through the public API with HOST (pinned) buffers, copies inside the timed region ----
     e2e_in = {k: torch.empty_like(v, device=dev).requires_grad_(True) for k, v in host_in.items()}
     out_host = {k: torch.empty_like(v).pin_memory() for k, v in host_in.items()}
-    img_host = torch.empty(VIEWS, 5, H, W).pin_memory()
+    img_host = [torch.empty(VIEWS, c, H, W).pin_memory() for c in (3, 1, 1)]
     h2d = sum(v.numel() * 4 for v in host_in.values()) + (gC_h.numel() + gD_h.numel() + gA_h.numel()) * 4
-    d2h = sum(v.numel() * 4 for v in out_host.values()) + img_host.numel() * 4
+    d2h = sum(v.numel() * 4 for v in out_host.values()) + sum(t.numel() for t in img_host) * 4
 
     def e2e_step():
         with torch.no_grad():
@@ -241,22 +303,14 @@ def run_ours(args):
         with torch.no_grad():
             for k in out_host:
                 out_host[k].copy_(grads[k], non_blocking=True)
-            img_host[:, 0:3].copy_(color, non_blocking=True)
-            img_host[:, 3:4].copy_(depth, non_blocking=True)
-            img_host[:, 4:5].copy_(alpha, non_blocking=True)
+            img_host[0].copy_(color, non_blocking=True)
+            img_host[1].copy_(depth, non_blocking=True)
+            img_host[2].copy_(alpha, non_blocking=True)
 
-    for _ in range(3):
-        e2e_step()
-    barrier()
+    log("e2e")
+    run_e2e, _ = make_runner(e2e_step)
     e_steps = max(3, min(args.steps, 10))
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e_steps)]
-    for i in range(e_steps):
-        flush_buf.zero_()
-        ev2[i][0].record()
-        e2e_step()
-        ev2[i][1].record()
-    barrier()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    e2e_ms = timed(run_e2e, e_steps)
     clocks = sampler.result()
 
     # ---- max over ranks ----
@@ -291,6 +345,7 @@ def run_ours(args):
             roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 4), "traffic": traffic, "algorithmic_bytes": ab,
                     "launch_ms": round(dur * 1e3, 4), "peak_source": peak_src}
+        log("cpu baseline")
         cpu = cpu_baseline_sample(host_in, cams, P, views=1 if not args.small else 1)
         out = {
             "metric": "rasterize fwd+bwd Gaussians/s @512x512, 8 views/GPU", "value": value, "unit": "Gaussians/s",
@@ -300,10 +355,11 @@ def run_ours(args):
                        "P": P, "views_per_gpu": VIEWS, "H": H, "W": W, "num_rendered": n_r,
                        "l2": "flushed between steps (256 MiB write, outside the per-step events)",
                        "timing": "CUDA events per step on the launch stream, summed over K steps, max over ranks",
+                       "launch": "eager" if args.no_graph else "one CUDA-graph replay per step (forward+backward+exchange captured through the public API)",
                        "exchange": "none" if world == 1 else "NCCL all-reduce of time-invariant attribute grads (8.4 MB) per step"},
             "e2e": {"value": e2e_value, "unit": "Gaussians/s", "ms_per_step": e2e_ms_per_step,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps},
-            "gpu_launches": int(sum(n for _, n in prof.values())),
+            "gpu_launches": launches_per_step * args.steps,
             "kernels": kern, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
         }
     if dist is not None:
@@ -346,7 +402,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return None
-    scene, gs, cams = build_workload(0, args.small)
+    scene, graph, node = build_scene(args.small)
+    cams = build_cameras(0)
+    gs = gaussian_sets_oracle(scene, graph, node)
     host_in = dict(means=gs["means3D"], rots=gs["rotations"], scales=gs["scales"], opac=gs["opacities"], cols=gs["colors"])
     P = host_in["means"].shape[1]
     for _ in range(min(args.warmup, 1)):
