@@ -1,0 +1,121 @@
+"""GPU end-to-end: deformation network -> fused skinning -> 6-channel batched rasterizer -> post-ops
+(DiffGaussianBatchRenderer.batch_forward) against the oracle chain (CPU copy of the network -> skin oracle ->
+C rasterizer oracle per view -> the same post-ops restated in torch), forward and full-chain gradients."""
+import copy
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dreammesh4d_b200 import synthetic
+from dreammesh4d_b200.camera import get_cam_info_gaussian
+from dreammesh4d_b200.deformation import HexPlaneDeformation
+from dreammesh4d_b200.geometry import DynamicSuGaRGeometry, activate_node_deltas
+from dreammesh4d_b200.renderer import DiffGaussianBatchRenderer, depth_to_normal
+from oracle import skin_oracle as SO
+from oracle.raster_oracle import RasterOracle
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def make_rays(c2w, fovy, H, W):
+    """threestudio get_ray_directions (pixel centres, z=-1) + get_rays without normalisation (T/utils/ops.py:197-260)."""
+    focal = 0.5 * H / torch.tan(0.5 * fovy)
+    j, i = torch.meshgrid(torch.arange(H, dtype=torch.float32) + 0.5, torch.arange(W, dtype=torch.float32) + 0.5, indexing="ij")
+    d = torch.stack([(i[None] - W / 2) / focal[:, None, None], -(j[None] - H / 2) / focal[:, None, None],
+                     -torch.ones(len(fovy), H, W)], dim=-1)
+    rays_d = (d[..., None, :] * c2w[:, None, None, :3, :3]).sum(-1)
+    rays_o = c2w[:, None, None, :3, 3].expand_as(rays_d)
+    return rays_o.contiguous(), rays_d.contiguous()
+
+
+def test_batch_forward_matches_oracle_chain():
+    torch.manual_seed(0)
+    B, H, W = 3, 96, 96
+    scene = synthetic.make_sugar_scene(1_200, g=3)
+    graph = synthetic.make_deform_graph(scene.verts, 24, 4)
+    net = HexPlaneDeformation()
+    with torch.no_grad():   # make the zero-initialised heads produce a visible deformation
+        for head, s in ((net.deformation_net.pos_deform, 0.02), (net.deformation_net.rotations_deform, 0.1),
+                        (net.deformation_net.scales_deform, 0.03), (net.deformation_net.opacity_deform, 0.5)):
+            head.feature_out[1].weight.normal_(0, s)
+    net_cpu = copy.deepcopy(net)
+    geo = DynamicSuGaRGeometry(scene, graph, net).to(DEV)
+    ren = DiffGaussianBatchRenderer(geo)
+    c2w, fovy = synthetic.random_orbit_cameras(B, seed=8)
+    rays_o, rays_d = make_rays(c2w, fovy, H, W)
+    ts = torch.linspace(0, 1, B + 2)[1:-1]
+    batch = {"c2w": c2w.to(DEV), "fovy": fovy.to(DEV), "height": H, "width": W, "timestamp": ts.to(DEV),
+             "rays_o": rays_o.to(DEV), "rays_d": rays_d.to(DEV)}
+    geo.update_step(0, 0)
+    out = ren.batch_forward(batch)
+
+    # ---- oracle chain ----
+    node = activate_node_deltas(*net_cpu(graph.node_xyz, ts))
+    ref = SO.deform_gaussians(scene, graph, *node)
+    Vm, PV, campos, tanx, tany = get_cam_info_gaussian(c2w, fovy, fovy)
+    P = scene.n_gaussians
+    orc, oks = [], []
+    color6 = torch.zeros(B, 6, H, W); depth = torch.zeros(B, 1, H, W); alpha = torch.zeros(B, 1, H, W)
+    for v in range(B):
+        o = RasterOracle(P, H, W, 6, "f32")
+        feat = torch.cat([ref["colors"], ref["normals"][v]], dim=1).detach()
+        c, r, d, a = o.forward(ref["means3D"][v].detach().numpy(), ref["scales"].detach().numpy(), ref["rotations"][v].detach().numpy(),
+                               ref["opacities"].detach().numpy(), feat.numpy(), Vm[v].numpy(), PV[v].numpy(), float(tanx[v]),
+                               float(tany[v]), np.ones(6, np.float32))
+        color6[v], depth[v], alpha[v] = torch.from_numpy(c), torch.from_numpy(d), torch.from_numpy(a)
+        orc.append(o)
+        ok = torch.from_numpy(~o.ambiguous)
+        # a pixel is comparable if neither it nor its 4-neighbourhood (depth stencil) is ambiguous, and it does
+        # not sit on the alpha>0.99 mask threshold
+        okp = F.pad(ok[None, None].float(), (1, 1, 1, 1), value=1.0)
+        ok = ok & (okp[0, 0, 1:-1, 2:] > 0) & (okp[0, 0, 1:-1, :-2] > 0) & (okp[0, 0, 2:, 1:-1] > 0) & (okp[0, 0, :-2, 1:-1] > 0)
+        ok = ok & ((alpha[v, 0] - 0.99).abs() > 1e-4)
+        oks.append(ok)
+        assert np.array_equal(out["radii"][v].cpu().numpy(), r)
+    ok = torch.stack(oks)[:, None]
+    mask = alpha > 0.99
+    xyz = rays_o.permute(0, 3, 1, 2) + depth * rays_d.permute(0, 3, 1, 2)
+    nfd = F.normalize(depth_to_normal(xyz), dim=1) * 0.5 * alpha + 0.5
+    nrm = F.normalize(color6[:, 3:], dim=1) * 0.5 * alpha + 0.5
+    expect = {"comp_rgb": color6[:, :3].clamp(0, 1), "comp_depth": depth, "comp_mask": alpha, "comp_normal": nrm,
+              "comp_normal_from_dist": nfd}
+    tol = {"comp_rgb": 1e-4, "comp_depth": 1e-4, "comp_mask": 1e-4, "comp_normal": 2e-4, "comp_normal_from_dist": 2e-3}
+    for k, want in expect.items():
+        got = out[k].detach().cpu().permute(0, 3, 1, 2)
+        m = ok.expand_as(want)
+        if k == "comp_normal_from_dist":     # finite differences of depth: only meaningful inside the surface
+            inner = F.avg_pool2d(mask.float(), 3, 1, 1) > 0.999
+            m = m & inner.expand_as(want)
+        err = ((got - want).abs() * m).max().item() / max(want.abs().max().item(), 1e-30)
+        assert err <= tol[k], f"{k}: rel Linf {err}"
+
+    # ---- full-chain gradients: d loss / d network parameters ----
+    g = torch.Generator().manual_seed(1)
+    gC = torch.randn(B, 3, H, W, generator=g) * ok
+    gA = torch.randn(B, 1, H, W, generator=g) * ok
+    # keep the clamp inactive region only (clamp(0,1) has zero gradient outside)
+    inside = ((color6[:, :3] > 0) & (color6[:, :3] < 1)).float()
+    loss = (out["comp_rgb"].permute(0, 3, 1, 2) * (gC * inside).to(DEV)).sum() + (out["comp_mask"].permute(0, 3, 1, 2) * gA.to(DEV)).sum()
+    loss.backward()
+    g_means, g_rots = [], []
+    for v in range(B):
+        g6 = torch.cat([gC[v] * inside[v], torch.zeros(3, H, W)], dim=0)
+        gr = orc[v].backward(g6.numpy(), None, gA[v].numpy())
+        g_means.append(torch.from_numpy(gr["means3D"]))
+        g_rots.append(torch.from_numpy(gr["rotations"]))
+    torch.autograd.backward([ref["means3D"], ref["rotations"]], [torch.stack(g_means), torch.stack(g_rots)])
+    checked = 0
+    for (name, p_gpu), (_, p_cpu) in zip(net.named_parameters(), net_cpu.named_parameters()):
+        if p_cpu.grad is None or float(p_cpu.grad.abs().max()) == 0:
+            continue
+        err = Hh.rel_linf(p_gpu.grad.cpu().numpy(), p_cpu.grad.numpy())
+        assert err <= 2e-3, f"grad {name}: rel Linf {err}"
+        checked += 1
+    assert checked >= 8
+    # screen-space mean gradients are exposed like the reference's viewspace_points
+    assert out["viewspace_points"].grad is not None and out["viewspace_points"].grad.shape == (B, P, 3)
