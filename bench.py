@@ -345,8 +345,10 @@ def run_ours(args):
             roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 4), "traffic": traffic, "algorithmic_bytes": ab,
                     "launch_ms": round(dur * 1e3, 4), "peak_source": peak_src}
-        log("cpu baseline")
-        cpu = cpu_baseline_sample(host_in, cams, P, views=1 if not args.small else 1)
+        cpu = None
+        if world == 1:       # reported baseline: rank 0 at N=1 only
+            log("cpu baseline")
+            cpu = cpu_baseline_sample(host_in, cams, P, views=1)
         out = {
             "metric": "rasterize fwd+bwd Gaussians/s @512x512, 8 views/GPU", "value": value, "unit": "Gaussians/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -362,10 +364,12 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "kernels": kern, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
         }
+    if out is not None:
+        print(json.dumps(out), flush=True)
     if dist is not None:
-        dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
-    return out
+    return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -428,6 +432,9 @@ def run_reference(args):
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(420, exit=True)      # never hang a GPU box: dump stacks and exit after 7 min
     args = parse()
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:

@@ -25,7 +25,7 @@ void raster_sizes(int P, int H, int W, int n_views, int channels, long long capa
     const int rec = rec_floats(channels), acc = acc_floats(channels);
     if (geom) *geom = 256 + align_up(np * rec * 4, 256) + align_up(np * 4, 256);   // never zero-sized
     if (bin)
-        *bin = 256 + align_up(nt * 4, 256) + align_up((nt + 1) * 4, 256) + align_up(nt * 4, 256) +
+        *bin = 256 + align_up(nt * 4, 256) + align_up((nt + 1) * 4, 256) + align_up(nt * 4, 256) + align_up(nt * 4, 256) +
                align_up((uint64_t)capacity * 8, 256) + align_up((uint64_t)capacity * rec * 4, 256);
     if (img) *img = align_up((uint64_t)n_views * H * W * 4, 256);
     if (bwd) *bwd = 256 + align_up(np * acc * 4, 256);
@@ -72,6 +72,7 @@ int raster_make_layout(const dm4d_raster_desc* d, RasterLayout* L) {
     L->tile_count = (unsigned int*)p; p += align_up(nt * 4, 256);
     L->tile_offset = (unsigned int*)p; p += align_up((nt + 1) * 4, 256);
     L->tile_cursor = (unsigned int*)p; p += align_up(nt * 4, 256);
+    L->tile_order = (unsigned int*)p; p += align_up(nt * 4, 256);
     L->keys = (unsigned long long*)p; p += align_up((uint64_t)L->capacity * 8, 256);
     L->stream = (float*)p;
     L->n_contrib = (unsigned int*)d->img;

@@ -21,6 +21,7 @@ constexpr int SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(RasterLayout L) {
     __shared__ unsigned int warp_sums[SCAN_THREADS / 32];
     __shared__ unsigned int carry_s;
+    __shared__ unsigned int bucket_cnt[33], bucket_pos[33];
     const int n = L.n_views * L.tiles;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
@@ -60,6 +61,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(RasterLayout L
         L.hdr->total = total;
         L.hdr->overflow = ((long long)total > L.capacity) ? 1u : 0u;
     }
+    // Launch order of the per-tile CTAs: heaviest tiles first (counting sort on floor(log2(count))), so the
+    // long limb/centre tiles do not form the tail of the render kernels.
+    if (tid < 33) bucket_cnt[tid] = 0u;
+    __syncthreads();
+    for (int i = beg; i < end; ++i) atomicAdd(&bucket_cnt[32 - __clz(L.tile_count[i])], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int run2 = 0;
+        for (int b = 32; b >= 0; --b) { bucket_pos[b] = run2; run2 += bucket_cnt[b]; }
+    }
+    __syncthreads();
+    for (int i = beg; i < end; ++i) L.tile_order[atomicAdd(&bucket_pos[32 - __clz(L.tile_count[i])], 1u)] = (unsigned int)i;
 }
 
 __global__ void __launch_bounds__(DM4D_BLOCK) scatter_kernel(RasterLayout L) {
@@ -71,7 +84,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK) scatter_kernel(RasterLayout L) {
     const int v = (int)(idx / L.P);
     const unsigned int g = (unsigned int)(idx - (long long)v * L.P);
     const int minx = rect & 0xff, miny = (rect >> 8) & 0xff, maxx = (rect >> 16) & 0xff, maxy = rect >> 24;
-    const float depth = L.g_rec[(size_t)idx * L.rec + 6];
+    const float depth = L.g_rec[(size_t)idx * L.rec + rec_depth_index(L.channels)];
     const unsigned long long key = ((unsigned long long)__float_as_uint(depth) << 32) | g;
     const size_t tbase = (size_t)v * L.tiles;
     for (int y = miny; y < maxy; ++y)
@@ -122,10 +135,29 @@ __device__ void smem_network(unsigned long long* sk, int cn /* pow2 <= SORT_CHUN
     }
 }
 
+// Copies one projected record into the sorted stream, replacing the contribution half-height by the
+// tile-local row mask: bit r set <=> some pixel of row tile_y0 + r can reach alpha >= 1/255.
+__device__ __forceinline__ void pack_record(const float4* __restrict__ src, float4* __restrict__ dst, int r4, float tile_y0) {
+    const float4 a = src[0];
+    float4 b = src[1];
+    const float ey = b.z;
+    unsigned int mask = 0u;
+    if (ey > 0.f) {
+        const float lo = a.y - ey - tile_y0, hi = a.y + ey - tile_y0;      // contributing rows: lo <= r <= hi
+        const int r0 = lo <= 0.f ? 0 : (lo >= 16.f ? 16 : (int)ceilf(lo));
+        const int r1 = hi >= 15.f ? 15 : (hi < 0.f ? -1 : (int)floorf(hi));
+        if (r1 >= r0) mask = ((2u << r1) - 1u) & ~((1u << r0) - 1u);
+    }
+    b.z = __uint_as_float(mask);
+    dst[0] = a;
+    dst[1] = b;
+    for (int q = 2; q < r4; ++q) dst[q] = src[q];
+}
+
 __global__ void __launch_bounds__(DM4D_BLOCK) sort_pack_kernel(RasterLayout L) {
     __shared__ unsigned long long sk[SORT_CHUNK];
     if (L.hdr->overflow) return;
-    const int tile = blockIdx.x;                 // global (view, tile) index
+    const int tile = (int)L.tile_order[blockIdx.x];   // global (view, tile) index, heaviest first
     const unsigned int beg = L.tile_offset[tile];
     const int n = (int)(L.tile_offset[tile + 1] - beg);
     if (n == 0) return;
@@ -137,6 +169,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK) sort_pack_kernel(RasterLayout L) {
     const float4* grec = reinterpret_cast<const float4*>(L.g_rec + (size_t)v * L.P * L.rec);
     float4* srec = reinterpret_cast<float4*>(L.stream + (size_t)beg * L.rec);
     const int r4 = L.rec / 4;
+    const float tile_y0 = (float)(((tile - v * L.tiles) / L.gx) * DM4D_TILE);
 
     if (npow2 <= SORT_CHUNK) {
         for (int i = threadIdx.x; i < npow2; i += blockDim.x) sk[i] = i < n ? gk[i] : KEY_INF;
@@ -144,9 +177,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK) sort_pack_kernel(RasterLayout L) {
         smem_network(sk, npow2, 2, npow2);
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const unsigned int id = (unsigned int)(sk[i] & 0xffffffffull);
-            const float4* src = grec + (size_t)id * r4;
-            float4* dst = srec + (size_t)i * r4;
-            for (int q = 0; q < r4; ++q) dst[q] = src[q];
+            pack_record(grec + (size_t)id * r4, srec + (size_t)i * r4, r4, tile_y0);
         }
         return;
     }
@@ -192,9 +223,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK) sort_pack_kernel(RasterLayout L) {
     }
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const unsigned int id = (unsigned int)(gk[i] & 0xffffffffull);
-        const float4* src = grec + (size_t)id * r4;
-        float4* dst = srec + (size_t)i * r4;
-        for (int q = 0; q < r4; ++q) dst[q] = src[q];
+        pack_record(grec + (size_t)id * r4, srec + (size_t)i * r4, r4, tile_y0);
     }
 }
 

@@ -14,9 +14,13 @@ struct BinHeader {
 
 // Projected per-(view, Gaussian) record; also the element of the sorted instance stream.
 //   f[0..3]  = x, y, conic.x, conic.y
-//   f[4..7]  = conic.z, opacity, depth, id (int bits)
-//   f[8..]   = `channels` feature floats, zero-padded to a multiple of 4
+//   f[4..7]  = conic.z, opacity, W, id (int bits)
+//              W = per-Gaussian contribution half-height `ey` in pixels (geom records), replaced per
+//              (instance, tile) by the 16-bit tile-local ROW MASK of rows that can reach alpha >= 1/255
+//              (instance stream)
+//   3 ch: f[8..11]  = r, g, b, depth            6 ch: f[8..15] = r, g, b, n0, n1, n2, depth, 0
 __host__ __device__ inline int rec_floats(int channels) { return channels <= 3 ? 12 : 16; }
+__host__ __device__ inline int rec_depth_index(int channels) { return channels <= 3 ? 11 : 14; }
 // Backward accumulator row per (view, Gaussian):
 //   [0..1] dL/dmean2D, [2..4] dL/dconic (x, y(half), z), [5] dL/dopacity, [6] dL/ddepth, [7] pad,
 //   [8..8+C) dL/dfeature, padded to a multiple of 4
@@ -33,6 +37,7 @@ struct RasterLayout {
     unsigned int* tile_count;   // [n_views*tiles]
     unsigned int* tile_offset;  // [n_views*tiles + 1]
     unsigned int* tile_cursor;  // [n_views*tiles]
+    unsigned int* tile_order;   // [n_views*tiles] (view,tile) indices, heaviest tiles first (CTA launch order)
     unsigned long long* keys;   // [capacity]  (depth bits << 32) | gaussian id
     float* stream;              // [capacity*rec] sorted instance records
     // img

@@ -142,16 +142,26 @@ __global__ void __launch_bounds__(DM4D_BLOCK) preprocess_kernel(PreArgs a) {
     a.g_rect[idx] = (unsigned)rminx | ((unsigned)rminy << 8) | ((unsigned)rmaxx << 16) | ((unsigned)rmaxy << 24);
 
     const float op = a.opacities[set * a.opacities_stride + g];
+    // Half-height (pixels) of the region where alpha = op*exp(power) can reach 1/255:
+    // max_x power(dx, dy) = -0.5 dy^2 det(conic)/conic.x >= -ln(255 op).  Conservative (margins cover the
+    // render kernels' rounding); <= 0 means the Gaussian can never contribute; huge means "no information".
+    float ey = 0.f;
+    {
+        const float t = logf(255.0f * op) + 1e-4f;
+        const float detc = conx * conz - cony * cony;
+        if (t > 0.f) ey = (detc > 0.f && conx > 0.f) ? sqrtf(2.0f * t * conx / detc) * 1.001f + 1e-3f : 1e30f;
+        if (!(ey == ey)) ey = 1e30f;
+    }
     float4* rec = reinterpret_cast<float4*>(a.g_rec + (size_t)idx * a.rec);
     rec[0] = make_float4(ix, iy, conx, cony);
-    rec[1] = make_float4(conz, op, pr.tz, __int_as_float(g));
+    rec[1] = make_float4(conz, op, ey, __int_as_float(g));
     const float* c0 = a.colors + set * a.colors_stride + (size_t)g * 3;
     if (a.channels <= 3) {
-        rec[2] = make_float4(c0[0], c0[1], c0[2], 0.f);
+        rec[2] = make_float4(c0[0], c0[1], c0[2], pr.tz);
     } else {
         const float* c1 = a.colors2 + set * a.colors2_stride + (size_t)g * 3;
         rec[2] = make_float4(c0[0], c0[1], c0[2], c1[0]);
-        rec[3] = make_float4(c1[1], c1[2], 0.f, 0.f);
+        rec[3] = make_float4(c1[1], c1[2], pr.tz, 0.f);
     }
 
     unsigned int* cnt = a.tile_count + (size_t)v * a.tiles;

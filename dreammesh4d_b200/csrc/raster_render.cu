@@ -59,19 +59,26 @@ struct RecTraits {
     static constexpr int ACC = C <= 3 ? 12 : 16;   // floats per accumulator row
 };
 
+// features + depth of one record (layout: raster_internal.cuh)
 template <int C>
-__device__ __forceinline__ void load_features(const float4* r, float (&f)[C]) {
+__device__ __forceinline__ void load_features(const float4* r, float (&f)[C], float& depth) {
     const float4 c0 = r[2];
     f[0] = c0.x; f[1] = c0.y; f[2] = c0.z;
     if constexpr (C > 3) {
         const float4 c1 = r[3];
         f[3] = c0.w; f[4] = c1.x; f[5] = c1.y;
+        depth = c1.z;
+    } else {
+        depth = c0.w;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// Each warp owns two pixel rows of the tile (16 x 2).  For every group of 32 staged instances the
+// lanes test the instances' row masks against the warp's rows and ballot: the warp then walks only
+// the set bits, i.e. only instances that can reach alpha >= 1/255 somewhere in its two rows.
 template <int C>
 __global__ void __launch_bounds__(CHUNK) render_forward_kernel(RasterLayout L, const float* __restrict__ view_params,
                                                                 float* __restrict__ out_color,
@@ -82,13 +89,14 @@ __global__ void __launch_bounds__(CHUNK) render_forward_kernel(RasterLayout L, c
     float4* buf = reinterpret_cast<float4*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)FWD_STAGES * CHUNK * TR::REC * sizeof(float));
 
-    const int gt = blockIdx.x;
+    const int gt = (int)L.tile_order[blockIdx.x];
     const int v = gt / L.tiles, t = gt - v * L.tiles;
     const int tile_x = t % L.gx, tile_y = t / L.gx;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int px = tile_x * DM4D_TILE + (tid & 15), py = tile_y * DM4D_TILE + (tid >> 4);
     const bool inside = px < L.W && py < L.H;
     const float pfx = (float)px, pfy = (float)py;
+    const unsigned int my_rows = 3u << (2 * (tid >> 5));
 
     const unsigned int beg = L.tile_offset[gt];
     const int n = L.hdr->overflow ? 0 : (int)(L.tile_offset[gt + 1] - beg);
@@ -111,11 +119,12 @@ __global__ void __launch_bounds__(CHUNK) render_forward_kernel(RasterLayout L, c
         for (int c = 0; c < min(FWD_STAGES, nchunks); ++c) issue(c);
 
     bool done = !inside;
+    bool warp_done = __all_sync(0xffffffffu, done);
     float T = 1.0f, D = 0.f, Wg = 0.f;
     float Cacc[C];
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) Cacc[ch] = 0.f;
-    unsigned int contributor = 0, last = 0;
+    unsigned int last = 0;
 
     int c = 0;
     for (; c < nchunks; ++c) {
@@ -123,26 +132,35 @@ __global__ void __launch_bounds__(CHUNK) render_forward_kernel(RasterLayout L, c
         mbar_wait(&full[s], (uint32_t)(c / FWD_STAGES) & 1u);
         const int cnt = min(CHUNK, n - c * CHUNK);
         const float4* r = buf + (size_t)s * CHUNK * TR::R4;
-        for (int j = 0; !done && j < cnt; ++j) {
-            contributor++;
-            const float4 a = r[j * TR::R4 + 0];
-            const float4 b = r[j * TR::R4 + 1];
-            const float dx = a.x - pfx, dy = a.y - pfy;
-            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-            if (power > 0.0f) continue;
-            const float alpha = fminf(0.99f, b.y * expf(power));
-            if (alpha < 1.0f / 255.0f) continue;
-            const float test_T = T * (1.0f - alpha);
-            if (test_T < 0.0001f) { done = true; continue; }
-            float f[C];
-            load_features<C>(r + j * TR::R4, f);
-            const float w = alpha * T;
+        for (int g0 = 0; g0 < cnt && !warp_done; g0 += 32) {
+            const int jj = g0 + lane;
+            const unsigned int m = jj < cnt ? __float_as_uint(r[jj * TR::R4 + 1].z) : 0u;
+            unsigned int bal = __ballot_sync(0xffffffffu, (m & my_rows) != 0u);
+            while (bal) {
+                const int j = g0 + __ffs(bal) - 1;
+                bal &= bal - 1;
+                if (done) continue;
+                const float4* rp = r + j * TR::R4;
+                const float4 a = rp[0];
+                const float4 b = rp[1];
+                const float dx = a.x - pfx, dy = a.y - pfy;
+                const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+                if (power > 0.0f) continue;
+                const float alpha = fminf(0.99f, b.y * expf(power));
+                if (alpha < 1.0f / 255.0f) continue;
+                const float test_T = T * (1.0f - alpha);
+                if (test_T < 0.0001f) { done = true; continue; }
+                float f[C], dep;
+                load_features<C>(rp, f, dep);
+                const float w = alpha * T;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) Cacc[ch] += f[ch] * w;
-            D += b.z * w;
-            Wg += w;
-            T = test_T;
-            last = contributor;
+                for (int ch = 0; ch < C; ++ch) Cacc[ch] += f[ch] * w;
+                D += dep * w;
+                Wg += w;
+                T = test_T;
+                last = (unsigned int)(c * CHUNK + j + 1);
+            }
+            warp_done = __all_sync(0xffffffffu, done);
         }
         const int ndone = __syncthreads_count(done ? 1 : 0);
         if (ndone == CHUNK) break;
@@ -168,10 +186,29 @@ __global__ void __launch_bounds__(CHUNK) render_forward_kernel(RasterLayout L, c
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_sum(float v) {
+// Sums 16 per-lane values across the warp with 16 shuffles (recursive halving): after the call the
+// lane pair (2k, 2k+1) holds the warp total of slot k.
+__device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    float w8[8], w4[4], w2[2];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    for (int i = 0; i < 8; ++i) {
+        const float send = b4 ? v[i] : v[i + 8], keep = b4 ? v[i + 8] : v[i];
+        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b3 ? w8[i] : w8[i + 4], keep = b3 ? w8[i + 4] : w8[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b2 ? w4[i] : w4[i + 2], keep = b2 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const float send = b1 ? w2[0] : w2[1], keep = b1 ? w2[1] : w2[0];
+    const float w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    return w1 + __shfl_xor_sync(0xffffffffu, w1, 1);
 }
 
 template <int C>
@@ -187,7 +224,7 @@ __global__ void __launch_bounds__(CHUNK) render_backward_kernel(RasterLayout L, 
     uint64_t* full = reinterpret_cast<uint64_t*>(sacc + (size_t)CHUNK * TR::ACC);
     __shared__ unsigned int s_max_contrib;
 
-    const int gt = blockIdx.x;
+    const int gt = (int)L.tile_order[blockIdx.x];
     const int v = gt / L.tiles, t = gt - v * L.tiles;
     const int tile_x = t % L.gx, tile_y = t / L.gx;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -196,6 +233,7 @@ __global__ void __launch_bounds__(CHUNK) render_backward_kernel(RasterLayout L, 
     const float pfx = (float)px, pfy = (float)py;
     const size_t npix = (size_t)L.H * L.W;
     const size_t pix = (size_t)py * L.W + px;
+    const unsigned int my_rows = 3u << (2 * (tid >> 5));
 
     const unsigned int beg = L.tile_offset[gt];
     const int n = L.hdr->overflow ? 0 : (int)(L.tile_offset[gt + 1] - beg);
@@ -210,12 +248,10 @@ __global__ void __launch_bounds__(CHUNK) render_backward_kernel(RasterLayout L, 
     }
     for (int i = tid; i < CHUNK * TR::ACC; i += CHUNK) sacc[i] = 0.f;
     __syncthreads();
-    {
-        unsigned int m = last_contributor;
+    unsigned int warp_last = last_contributor;      // last contributor over the warp's 32 pixels
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0 && m > 0) atomicMax(&s_max_contrib, m);
-    }
+    for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
+    if (lane == 0 && warp_last > 0) atomicMax(&s_max_contrib, warp_last);
     __syncthreads();
     const int max_contrib = (int)s_max_contrib;
     if (max_contrib == 0) return;
@@ -256,75 +292,76 @@ __global__ void __launch_bounds__(CHUNK) render_backward_kernel(RasterLayout L, 
         mbar_wait(&full[s], (uint32_t)(k / BWD_STAGES) & 1u);
         const int cnt = min(CHUNK, n - c * CHUNK);
         const float4* r = buf + (size_t)s * CHUNK * TR::R4;
-        for (int j = cnt - 1; j >= 0; --j) {
-            const unsigned int gi = (unsigned int)(c * CHUNK + j);
-            bool valid = gi < last_contributor;
-            float4 a, b;
-            float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
-            if (valid) {
-                a = r[j * TR::R4 + 0];
-                b = r[j * TR::R4 + 1];
-                dx = a.x - pfx; dy = a.y - pfy;
-                const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-                valid = !(power > 0.0f);
+        // this warp only needs instances in front of its own last contributor
+        const int wcnt = min(cnt, (int)warp_last - c * CHUNK);
+        for (int g0 = wcnt > 0 ? ((wcnt - 1) & ~31) : -1; g0 >= 0; g0 -= 32) {
+            const int jj = g0 + lane;
+            const unsigned int m = jj < wcnt ? __float_as_uint(r[jj * TR::R4 + 1].z) : 0u;
+            unsigned int bal = __ballot_sync(0xffffffffu, (m & my_rows) != 0u);
+            while (bal) {
+                const int bpos = 31 - __clz(bal);
+                bal &= ~(1u << bpos);
+                const int j = g0 + bpos;
+                const unsigned int gi = (unsigned int)(c * CHUNK + j);
+                const float4* rp = r + j * TR::R4;
+                bool valid = gi < last_contributor;
+                float4 a, b;
+                float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
                 if (valid) {
-                    G = expf(power);
-                    alpha = fminf(0.99f, b.y * G);
-                    valid = !(alpha < 1.0f / 255.0f);
+                    a = rp[0];
+                    b = rp[1];
+                    dx = a.x - pfx; dy = a.y - pfy;
+                    const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+                    valid = !(power > 0.0f);
+                    if (valid) {
+                        G = expf(power);
+                        alpha = fminf(0.99f, b.y * G);
+                        valid = !(alpha < 1.0f / 255.0f);
+                    }
                 }
-            }
-            if (!__any_sync(0xffffffffu, valid)) continue;
+                if (!__any_sync(0xffffffffu, valid)) continue;
 
-            float g_m2x = 0.f, g_m2y = 0.f, g_cx = 0.f, g_cy = 0.f, g_cz = 0.f, g_op = 0.f, g_dep = 0.f;
-            float g_col[C];
+                // slots: 0-1 dmean2D, 2-4 dconic, 5 dopacity, 6 ddepth, 7 #contributing pixels, 8.. dfeatures
+                float gv[16];
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) g_col[ch] = 0.f;
-            if (valid) {
-                T = T / (1.0f - alpha);
-                const float w = alpha * T;
-                float f[C];
-                load_features<C>(r + j * TR::R4, f);
-                float dL_dalpha = 0.f;
+                for (int i = 0; i < 16; ++i) gv[i] = 0.f;
+                if (valid) {
+                    T = T / (1.0f - alpha);
+                    const float w = alpha * T;
+                    float f[C], dep;
+                    load_features<C>(rp, f, dep);
+                    float dL_dalpha = 0.f;
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) {
-                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                    last_color[ch] = f[ch];
-                    dL_dalpha += (f[ch] - accum_rec[ch]) * gC[ch];
-                    g_col[ch] = w * gC[ch];
+                    for (int ch = 0; ch < C; ++ch) {
+                        accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                        last_color[ch] = f[ch];
+                        dL_dalpha += (f[ch] - accum_rec[ch]) * gC[ch];
+                        gv[8 + ch] = w * gC[ch];
+                    }
+                    accum_d = last_alpha * last_depth + (1.f - last_alpha) * accum_d;
+                    last_depth = dep;
+                    dL_dalpha += (dep - accum_d) * gD;
+                    gv[6] = w * gD;
+                    accum_a = last_alpha + (1.f - last_alpha) * accum_a;
+                    dL_dalpha += (1.f - accum_a) * gA;
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                    const float dL_dG = b.y * dL_dalpha;
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * a.z - gdy * a.w;
+                    const float dG_ddely = -gdy * b.x - gdx * a.w;
+                    gv[0] = dL_dG * dG_ddelx * ddelx_dx;
+                    gv[1] = dL_dG * dG_ddely * ddely_dy;
+                    gv[2] = -0.5f * gdx * dx * dL_dG;
+                    gv[3] = -0.5f * gdx * dy * dL_dG;
+                    gv[4] = -0.5f * gdy * dy * dL_dG;
+                    gv[5] = G * dL_dalpha;
+                    gv[7] = 1.0f;
                 }
-                accum_d = last_alpha * last_depth + (1.f - last_alpha) * accum_d;
-                last_depth = b.z;
-                dL_dalpha += (b.z - accum_d) * gD;
-                g_dep = w * gD;
-                accum_a = last_alpha + (1.f - last_alpha) * accum_a;
-                dL_dalpha += (1.f - accum_a) * gA;
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                const float dL_dG = b.y * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * a.z - gdy * a.w;
-                const float dG_ddely = -gdy * b.x - gdx * a.w;
-                g_m2x = dL_dG * dG_ddelx * ddelx_dx;
-                g_m2y = dL_dG * dG_ddely * ddely_dy;
-                g_cx = -0.5f * gdx * dx * dL_dG;
-                g_cy = -0.5f * gdx * dy * dL_dG;
-                g_cz = -0.5f * gdy * dy * dL_dG;
-                g_op = G * dL_dalpha;
-            }
-            g_m2x = warp_sum(g_m2x); g_m2y = warp_sum(g_m2y);
-            g_cx = warp_sum(g_cx); g_cy = warp_sum(g_cy); g_cz = warp_sum(g_cz);
-            g_op = warp_sum(g_op); g_dep = warp_sum(g_dep);
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) g_col[ch] = warp_sum(g_col[ch]);
-            if (lane == 0) {
-                float* row = sacc + (size_t)j * TR::ACC;
-                atomicAdd(row + 0, g_m2x); atomicAdd(row + 1, g_m2y);
-                atomicAdd(row + 2, g_cx); atomicAdd(row + 3, g_cy); atomicAdd(row + 4, g_cz);
-                atomicAdd(row + 5, g_op); atomicAdd(row + 6, g_dep);
-                row[7] = 1.0f;   // touched flag
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) atomicAdd(row + 8 + ch, g_col[ch]);
+                const float tot = warp_reduce_scatter16(gv, lane);
+                const int slot = lane >> 1;
+                if (!(lane & 1) && slot < TR::ACC) atomicAdd(sacc + (size_t)j * TR::ACC + slot, tot);
             }
         }
         __syncthreads();
