@@ -75,24 +75,54 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(RasterLayout L
     for (int i = beg; i < end; ++i) L.tile_order[atomicAdd(&bucket_pos[32 - __clz(L.tile_count[i])], 1u)] = (unsigned int)i;
 }
 
+constexpr int SMEM_TILES = 4096;
+
+// One thread per (view, Gaussian): drops (depth bits << 32 | id) into the segments of the tiles it touches.
+// Slots are reserved per block: shared-memory count per tile -> one global atomic per touched tile for the
+// block's base -> shared-memory atomics hand out the slots.  (Order inside a segment is irrelevant: the
+// per-tile sort orders on the full 64-bit key.)
 __global__ void __launch_bounds__(DM4D_BLOCK) scatter_kernel(RasterLayout L) {
+    __shared__ unsigned int hist[SMEM_TILES];
     if (L.hdr->overflow) return;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)L.n_views * L.P) return;
-    const unsigned int rect = L.g_rect[idx];
-    if (rect == 0u) return;
-    const int v = (int)(idx / L.P);
-    const unsigned int g = (unsigned int)(idx - (long long)v * L.P);
+    const long long total = (long long)L.n_views * L.P;
+    const long long first = (long long)blockIdx.x * blockDim.x;
+    const long long last = min(first + blockDim.x, total) - 1;
+    const long long idx = first + threadIdx.x;
+    const int v_first = (int)(first / L.P);
+    const bool use_smem = L.tiles <= SMEM_TILES && v_first == (int)(last / L.P);
+    const unsigned int rect = idx < total ? L.g_rect[idx] : 0u;
     const int minx = rect & 0xff, miny = (rect >> 8) & 0xff, maxx = (rect >> 16) & 0xff, maxy = rect >> 24;
-    const float depth = L.g_rec[(size_t)idx * L.rec + rec_depth_index(L.channels)];
-    const unsigned long long key = ((unsigned long long)__float_as_uint(depth) << 32) | g;
-    const size_t tbase = (size_t)v * L.tiles;
+    unsigned long long key = 0ull;
+    size_t tbase = 0;
+    if (rect) {
+        const int v = (int)(idx / L.P);
+        const unsigned int g = (unsigned int)(idx - (long long)v * L.P);
+        const float depth = L.g_rec[(size_t)idx * L.rec + rec_depth_index(L.channels)];
+        key = ((unsigned long long)__float_as_uint(depth) << 32) | g;
+        tbase = (size_t)v * L.tiles;
+    }
+    if (!use_smem) {
+        for (int y = miny; y < maxy; ++y)
+            for (int x = minx; x < maxx; ++x) {
+                const size_t t = tbase + (size_t)y * L.gx + x;
+                const unsigned int slot = atomicAdd(&L.tile_cursor[t], 1u);
+                L.keys[L.tile_offset[t] + slot] = key;
+            }
+        return;
+    }
+    for (int i = threadIdx.x; i < L.tiles; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
     for (int y = miny; y < maxy; ++y)
-        for (int x = minx; x < maxx; ++x) {
-            const size_t t = tbase + (size_t)y * L.gx + x;
-            const unsigned int slot = atomicAdd(&L.tile_cursor[t], 1u);
-            L.keys[L.tile_offset[t] + slot] = key;
-        }
+        for (int x = minx; x < maxx; ++x) atomicAdd(&hist[y * L.gx + x], 1u);
+    __syncthreads();
+    const size_t vb = (size_t)v_first * L.tiles;
+    for (int i = threadIdx.x; i < L.tiles; i += blockDim.x) {
+        const unsigned int c = hist[i];
+        if (c) hist[i] = L.tile_offset[vb + i] + atomicAdd(&L.tile_cursor[vb + i], c);   // absolute position of this block's run
+    }
+    __syncthreads();
+    for (int y = miny; y < maxy; ++y)
+        for (int x = minx; x < maxx; ++x) L.keys[atomicAdd(&hist[y * L.gx + x], 1u)] = key;
 }
 
 // ---- per-tile sort ------------------------------------------------------------------------------

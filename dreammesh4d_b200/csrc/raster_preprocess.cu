@@ -98,9 +98,10 @@ __device__ __forceinline__ bool project_gaussian(const float* __restrict__ vp, f
     return true;
 }
 
-__global__ void __launch_bounds__(DM4D_BLOCK) preprocess_kernel(PreArgs a) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)a.n_views * a.P) return;
+constexpr int SMEM_TILES = 4096;   // per-view tile histogram kept in shared memory (<= 1024x1024 px)
+
+// Projects one (view, Gaussian); returns the packed tile rect (0 = culled).
+__device__ __forceinline__ unsigned int preprocess_one(const PreArgs& a, long long idx) {
     const int v = (int)(idx / a.P);
     const int g = (int)(idx - (long long)v * a.P);
     const float* __restrict__ vp = a.view_params + (size_t)v * DM4D_VIEW_STRIDE;
@@ -119,10 +120,10 @@ __global__ void __launch_bounds__(DM4D_BLOCK) preprocess_kernel(PreArgs a) {
     Proj pr;
     if (!project_gaussian(vp, m[0], m[1], m[2], mod * sc[0], mod * sc[1], mod * sc[2], q[0], q[1], q[2], q[3],
                           focal_x, focal_y, pr))
-        return;
+        return 0u;
 
     const float det = pr.a * pr.c - pr.b * pr.b;
-    if (det == 0.0f) return;
+    if (det == 0.0f) return 0u;
     const float det_inv = 1.0f / det;
     const float conx = pr.c * det_inv, cony = -pr.b * det_inv, conz = pr.a * det_inv;
 
@@ -136,10 +137,11 @@ __global__ void __launch_bounds__(DM4D_BLOCK) preprocess_kernel(PreArgs a) {
     const int rminy = min(a.gy, max(0, (int)((iy - my_radius) / (float)DM4D_TILE)));
     const int rmaxx = min(a.gx, max(0, (int)((ix + my_radius + (float)(DM4D_TILE - 1)) / (float)DM4D_TILE)));
     const int rmaxy = min(a.gy, max(0, (int)((iy + my_radius + (float)(DM4D_TILE - 1)) / (float)DM4D_TILE)));
-    if ((rmaxx - rminx) * (rmaxy - rminy) == 0) return;
+    if ((rmaxx - rminx) * (rmaxy - rminy) == 0) return 0u;
 
     a.radii[idx] = (int32_t)my_radius;
-    a.g_rect[idx] = (unsigned)rminx | ((unsigned)rminy << 8) | ((unsigned)rmaxx << 16) | ((unsigned)rmaxy << 24);
+    const unsigned int rect = (unsigned)rminx | ((unsigned)rminy << 8) | ((unsigned)rmaxx << 16) | ((unsigned)rmaxy << 24);
+    a.g_rect[idx] = rect;
 
     const float op = a.opacities[set * a.opacities_stride + g];
     // Half-height (pixels) of the region where alpha = op*exp(power) can reach 1/255:
@@ -164,9 +166,44 @@ __global__ void __launch_bounds__(DM4D_BLOCK) preprocess_kernel(PreArgs a) {
         rec[3] = make_float4(c1[1], c1[2], pr.tz, 0.f);
     }
 
-    unsigned int* cnt = a.tile_count + (size_t)v * a.tiles;
-    for (int y = rminy; y < rmaxy; ++y)
-        for (int x = rminx; x < rmaxx; ++x) atomicAdd(&cnt[y * a.gx + x], 1u);
+    return rect;
+}
+
+// One thread per (view, Gaussian).  Instances per tile are counted in a per-block shared-memory histogram
+// (a block's 256 consecutive Gaussians are mesh-coherent and hit a few dozen tiles) and flushed with one
+// global atomic per touched tile; blocks that straddle two views or very large images count globally.
+__global__ void __launch_bounds__(DM4D_BLOCK) preprocess_kernel(PreArgs a) {
+    __shared__ unsigned int hist[SMEM_TILES];
+    const long long total = (long long)a.n_views * a.P;
+    const long long first = (long long)blockIdx.x * blockDim.x;
+    const long long last = min(first + blockDim.x, total) - 1;
+    const long long idx = first + threadIdx.x;
+    const int v_first = (int)(first / a.P);
+    const bool use_smem = a.tiles <= SMEM_TILES && v_first == (int)(last / a.P);
+    if (use_smem) {
+        for (int i = threadIdx.x; i < a.tiles; i += blockDim.x) hist[i] = 0u;
+        __syncthreads();
+    }
+    const unsigned int rect = idx < total ? preprocess_one(a, idx) : 0u;
+    if (rect) {
+        const int minx = rect & 0xff, miny = (rect >> 8) & 0xff, maxx = (rect >> 16) & 0xff, maxy = rect >> 24;
+        if (use_smem) {
+            for (int y = miny; y < maxy; ++y)
+                for (int x = minx; x < maxx; ++x) atomicAdd(&hist[y * a.gx + x], 1u);
+        } else {
+            unsigned int* cnt = a.tile_count + (size_t)(idx / a.P) * a.tiles;
+            for (int y = miny; y < maxy; ++y)
+                for (int x = minx; x < maxx; ++x) atomicAdd(&cnt[y * a.gx + x], 1u);
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        unsigned int* cnt = a.tile_count + (size_t)v_first * a.tiles;
+        for (int i = threadIdx.x; i < a.tiles; i += blockDim.x) {
+            const unsigned int c = hist[i];
+            if (c) atomicAdd(&cnt[i], c);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
