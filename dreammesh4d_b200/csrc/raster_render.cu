@@ -20,6 +20,7 @@ namespace {
 constexpr int CHUNK = 256;       // instances per shared-memory stage
 constexpr int FWD_STAGES = 3;
 constexpr int BWD_STAGES = 2;
+constexpr int FWD_UNROLL = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -137,28 +138,45 @@ __global__ void __launch_bounds__(CHUNK) render_forward_kernel(RasterLayout L, c
             const unsigned int m = jj < cnt ? __float_as_uint(r[jj * TR::R4 + 1].z) : 0u;
             unsigned int bal = __ballot_sync(0xffffffffu, (m & my_rows) != 0u);
             while (bal) {
-                const int j = g0 + __ffs(bal) - 1;
-                bal &= bal - 1;
-                if (done) continue;
-                const float4* rp = r + j * TR::R4;
-                const float4 a = rp[0];
-                const float4 b = rp[1];
-                const float dx = a.x - pfx, dy = a.y - pfy;
-                const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-                if (power > 0.0f) continue;
-                const float alpha = fminf(0.99f, b.y * expf(power));
-                if (alpha < 1.0f / 255.0f) continue;
-                const float test_T = T * (1.0f - alpha);
-                if (test_T < 0.0001f) { done = true; continue; }
-                float f[C], dep;
-                load_features<C>(rp, f, dep);
-                const float w = alpha * T;
+                // Take up to FWD_UNROLL candidates at once: their loads, power and exp are independent, only
+                // the blend below is sequential, so a lone warp (the tail of a heavy tile) is not latency-bound.
+                int js[FWD_UNROLL];
+                float al[FWD_UNROLL];
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) Cacc[ch] += f[ch] * w;
-                D += dep * w;
-                Wg += w;
-                T = test_T;
-                last = (unsigned int)(c * CHUNK + j + 1);
+                for (int u = 0; u < FWD_UNROLL; ++u) {
+                    js[u] = bal ? g0 + __ffs(bal) - 1 : -1;
+                    bal &= bal - 1;
+                }
+#pragma unroll
+                for (int u = 0; u < FWD_UNROLL; ++u) {
+                    al[u] = 0.f;
+                    if (js[u] >= 0 && !done) {
+                        const float4* rp = r + js[u] * TR::R4;
+                        const float4 a = rp[0];
+                        const float4 b = rp[1];
+                        const float dx = a.x - pfx, dy = a.y - pfy;
+                        const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+                        const float alpha = fminf(0.99f, b.y * expf(power));
+                        al[u] = (power > 0.0f || alpha < 1.0f / 255.0f) ? 0.f : alpha;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < FWD_UNROLL; ++u) {
+                    if (al[u] > 0.f && !done) {
+                        const float alpha = al[u];
+                        const float test_T = T * (1.0f - alpha);
+                        if (test_T < 0.0001f) { done = true; continue; }
+                        float f[C], dep;
+                        load_features<C>(r + js[u] * TR::R4, f, dep);
+                        const float w = alpha * T;
+#pragma unroll
+                        for (int ch = 0; ch < C; ++ch) Cacc[ch] += f[ch] * w;
+                        D += dep * w;
+                        Wg += w;
+                        T = test_T;
+                        last = (unsigned int)(c * CHUNK + js[u] + 1);
+                    }
+                }
             }
             warp_done = __all_sync(0xffffffffu, done);
         }
