@@ -154,6 +154,11 @@ def algorithmic_bytes(kernel: str, n: int, R: int, px: int, tiles: int) -> float
     }.get(kernel, 0.0)
 
 
+def dbg(msg):
+    if os.environ.get("DM4D_BENCH_DEBUG"):
+        log(f"[rank {os.environ.get('RANK', '0')}] {msg}")
+
+
 def log(msg):
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
@@ -211,19 +216,24 @@ def run_ours(args):
     capacity = int(n_rendered * 1.25) + 4096
     del st
 
-    def step(inp):
+    def local_step(inp):
+        """forward + backward of this rank's 8 views through the public API (CUDA-graph capturable)."""
         out_state = []
         color, radii, depth, alpha = R.rasterize_batch(inp["means"], inp["opac"], inp["scales"], inp["rots"],
                                                        inp["cols"], vp, H, W, capacity=capacity, distinct_sets=True,
                                                        state_out=out_state)
         torch.autograd.backward([color, depth, alpha], [gC, gD, gA])
         grads = {k: inp[k].grad for k in inp}
-        if dist is not None:   # exchange step: time-invariant attribute gradients (scale / opacity / colour)
-            flat = torch.cat([grads["scales"].reshape(-1), grads["opac"].reshape(-1), grads["cols"].reshape(-1)])
-            dist.all_reduce(flat)
         for k in inp:
             inp[k].grad = None
-        return color, depth, alpha, grads, out_state[0]
+        shared = torch.cat([grads["scales"].reshape(-1), grads["opac"].reshape(-1), grads["cols"].reshape(-1)]) \
+            if dist is not None else None
+        return color, depth, alpha, grads, shared, out_state[0]
+
+    def exchange(out):
+        """the path's one exchange step: NCCL sum of the time-invariant attribute gradients (eager, same stream)."""
+        if dist is not None:
+            dist.all_reduce(out[4])
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -246,27 +256,40 @@ def run_ours(args):
                 out = fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        dbg("runner warmed up")
         if args.no_graph:
             return fn, out
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             out = fn()
+        dbg("runner captured")
+        graph.replay()
+        torch.cuda.synchronize()
+        dbg("runner replayed once")
         return graph.replay, out
 
     def timed(run, n):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         barrier()
+        dbg("timed: start")
         for i in range(n):
             flush_buf.zero_()
             ev[i][0].record()
             run()
             ev[i][1].record()
+        dbg("timed: enqueued")
         barrier()
+        dbg("timed: done")
         return sum(a.elapsed_time(b) for a, b in ev)
 
     log("warm-up + capture")
     # ---- timed: K steps, CUDA events per step on the launch stream, L2 flushed between steps ----
-    run_step, step_out = make_runner(lambda: step(dev_in))
+    replay_step, step_out = make_runner(lambda: local_step(dev_in))
+
+    def run_step():
+        replay_step()
+        exchange(step_out)
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     total_ms = timed(run_step, args.steps)
@@ -281,7 +304,7 @@ def run_ours(args):
     prof_steps = max(3, min(args.steps, 10))
     for _ in range(prof_steps):
         flush_buf.zero_()
-        step(dev_in)
+        exchange(local_step(dev_in))
     torch.cuda.synchronize()
     prof = _lib.profile_collect()
     _lib.profile_enable(False)
@@ -299,18 +322,31 @@ def run_ours(args):
             for k in e2e_in:
                 e2e_in[k].copy_(host_in[k], non_blocking=True)
             gC.copy_(gC_h, non_blocking=True); gD.copy_(gD_h, non_blocking=True); gA.copy_(gA_h, non_blocking=True)
-        color, depth, alpha, grads, _ = step(e2e_in)
+        out = local_step(e2e_in)
+        color, depth, alpha, grads = out[:4]
         with torch.no_grad():
             for k in out_host:
                 out_host[k].copy_(grads[k], non_blocking=True)
             img_host[0].copy_(color, non_blocking=True)
             img_host[1].copy_(depth, non_blocking=True)
             img_host[2].copy_(alpha, non_blocking=True)
+        return out
 
     log("e2e")
-    run_e2e, _ = make_runner(e2e_step)
+    replay_e2e, e2e_out = make_runner(e2e_step)
+    log("e2e captured")
+
+    shared_host = None if dist is None else torch.empty(e2e_out[4].shape).pin_memory()
+
+    def run_e2e():
+        replay_e2e()
+        exchange(e2e_out)
+        if dist is not None:      # the exchanged (summed) gradients are what the step returns to the host
+            shared_host.copy_(e2e_out[4], non_blocking=True)
+
     e_steps = max(3, min(args.steps, 10))
     e2e_ms = timed(run_e2e, e_steps)
+    log(f"e2e done: {e2e_ms / e_steps:.3f} ms/step")
     clocks = sampler.result()
 
     # ---- max over ranks ----
@@ -357,7 +393,7 @@ def run_ours(args):
                        "P": P, "views_per_gpu": VIEWS, "H": H, "W": W, "num_rendered": n_r,
                        "l2": "flushed between steps (256 MiB write, outside the per-step events)",
                        "timing": "CUDA events per step on the launch stream, summed over K steps, max over ranks",
-                       "launch": "eager" if args.no_graph else "one CUDA-graph replay per step (forward+backward+exchange captured through the public API)",
+                       "launch": "eager" if args.no_graph else "one CUDA-graph replay per step (forward+backward captured through the public API); exchange launched eagerly after it",
                        "exchange": "none" if world == 1 else "NCCL all-reduce of time-invariant attribute grads (8.4 MB) per step"},
             "e2e": {"value": e2e_value, "unit": "Gaussians/s", "ms_per_step": e2e_ms_per_step,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps},
@@ -434,9 +470,14 @@ def run_reference(args):
 def main():
     import faulthandler
     faulthandler.enable()
-    faulthandler.dump_traceback_later(420, exit=True)      # never hang a GPU box: dump stacks and exit after 7 min
+    faulthandler.dump_traceback_later(int(os.environ.get("DM4D_BENCH_WATCHDOG_S", "420")), exit=True)   # never hang a GPU box
     args = parse()
-    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    try:
+        out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    except BaseException:
+        import traceback
+        log("FAILED rank %s:\n%s" % (os.environ.get("RANK", "0"), traceback.format_exc()))
+        raise
     if out is not None:
         print(json.dumps(out))
 

@@ -190,18 +190,37 @@ __device__ void smem_network(unsigned long long* sk, int cn /* pow2 <= SORT_CHUN
     }
 }
 
-// Copies one projected record into the sorted stream, replacing the contribution half-height by the
-// tile-local row mask: bit r set <=> some pixel of row tile_y0 + r can reach alpha >= 1/255.
-__device__ __forceinline__ void pack_record(const float4* __restrict__ src, float4* __restrict__ dst, int r4, float tile_y0) {
+// Minimum of q(x,y) = cx x^2 + 2 cy x y + cz y^2 (positive definite) over the rectangle [x0,x1] x [y0,y1].
+__device__ __forceinline__ float min_quad_rect(float cx, float cy, float cz, float x0, float x1, float y0, float y1) {
+    if (x0 <= 0.f && 0.f <= x1 && y0 <= 0.f && 0.f <= y1) return 0.f;
+    auto q = [&](float x, float y) { return cx * x * x + 2.f * cy * x * y + cz * y * y; };
+    const float icz = 1.f / cz, icx = 1.f / cx;
+    const float ya = fminf(fmaxf(-cy * x0 * icz, y0), y1), yb = fminf(fmaxf(-cy * x1 * icz, y0), y1);
+    const float xa = fminf(fmaxf(-cy * y0 * icx, x0), x1), xb = fminf(fmaxf(-cy * y1 * icx, x0), x1);
+    return fminf(fminf(q(x0, ya), q(x1, yb)), fminf(q(xa, y0), q(xb, y1)));
+}
+
+// Copies one projected record into the sorted stream, replacing the contribution threshold by the tile-local
+// strip mask: bit s set <=> some pixel of rows (2s, 2s+1) x the tile's 16 columns can reach alpha >= 1/255
+// (exact ellipse-vs-strip test, conservative by the margins; never drops a contributing pixel).
+__device__ __forceinline__ void pack_record(const float4* __restrict__ src, float4* __restrict__ dst, int r4,
+                                            float tile_x0, float tile_y0) {
     const float4 a = src[0];
     float4 b = src[1];
-    const float ey = b.z;
+    const float thr = b.z;
     unsigned int mask = 0u;
-    if (ey > 0.f) {
-        const float lo = a.y - ey - tile_y0, hi = a.y + ey - tile_y0;      // contributing rows: lo <= r <= hi
-        const int r0 = lo <= 0.f ? 0 : (lo >= 16.f ? 16 : (int)ceilf(lo));
-        const int r1 = hi >= 15.f ? 15 : (hi < 0.f ? -1 : (int)floorf(hi));
-        if (r1 >= r0) mask = ((2u << r1) - 1u) & ~((1u << r0) - 1u);
+    if (thr > 0.f) {
+        const float cx = a.z, cy = a.w, cz = b.x;
+        if (!(cx > 0.f) || !(cz > 0.f) || !(cx * cz - cy * cy > 0.f) || !(thr < 1e29f)) {
+            mask = 0xffu;
+        } else {
+            const float x0 = tile_x0 - a.x - 0.01f, x1 = tile_x0 + 15.f - a.x + 0.01f;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const float y0 = tile_y0 + (float)(2 * s) - a.y - 0.01f;
+                if (min_quad_rect(cx, cy, cz, x0, x1, y0, y0 + 1.02f) <= thr) mask |= 1u << s;
+            }
+        }
     }
     b.z = __uint_as_float(mask);
     dst[0] = a;
@@ -225,6 +244,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pack_kernel(RasterLayout L)
     float4* srec = reinterpret_cast<float4*>(L.stream + (size_t)beg * L.rec);
     const int r4 = L.rec / 4;
     const float tile_y0 = (float)(((tile - v * L.tiles) / L.gx) * DM4D_TILE);
+    const float tile_x0 = (float)(((tile - v * L.tiles) % L.gx) * DM4D_TILE);
 
     if (npow2 <= SORT_CHUNK) {
         for (int i = threadIdx.x; i < npow2; i += blockDim.x) sk[i] = i < n ? gk[i] : KEY_INF;
@@ -232,7 +252,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pack_kernel(RasterLayout L)
         smem_network(sk, npow2, 2, npow2);
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const unsigned int id = (unsigned int)(sk[i] & 0xffffffffull);
-            pack_record(grec + (size_t)id * r4, srec + (size_t)i * r4, r4, tile_y0);
+            pack_record(grec + (size_t)id * r4, srec + (size_t)i * r4, r4, tile_x0, tile_y0);
         }
         return;
     }
@@ -278,7 +298,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pack_kernel(RasterLayout L)
     }
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const unsigned int id = (unsigned int)(gk[i] & 0xffffffffull);
-        pack_record(grec + (size_t)id * r4, srec + (size_t)i * r4, r4, tile_y0);
+        pack_record(grec + (size_t)id * r4, srec + (size_t)i * r4, r4, tile_x0, tile_y0);
     }
 }
 

@@ -144,14 +144,14 @@ __device__ __forceinline__ unsigned int preprocess_one(const PreArgs& a, long lo
     a.g_rect[idx] = rect;
 
     const float op = a.opacities[set * a.opacities_stride + g];
-    // Half-height (pixels) of the region where alpha = op*exp(power) can reach 1/255:
-    // max_x power(dx, dy) = -0.5 dy^2 det(conic)/conic.x >= -ln(255 op).  Conservative (margins cover the
-    // render kernels' rounding); <= 0 means the Gaussian can never contribute; huge means "no information".
+    // Contribution threshold on the quadratic form q(d) = conic.x dx^2 + 2 conic.y dx dy + conic.z dy^2:
+    // alpha = op*exp(-q/2) can reach 1/255 only where q <= 2 ln(255 op).  Stored with a safety margin that
+    // covers the render kernels' rounding; <= 0 means the Gaussian can never contribute.  sort_pack turns it
+    // into the per-(instance, tile) strip mask.
     float ey = 0.f;
     {
-        const float t = logf(255.0f * op) + 1e-4f;
-        const float detc = conx * conz - cony * cony;
-        if (t > 0.f) ey = (detc > 0.f && conx > 0.f) ? sqrtf(2.0f * t * conx / detc) * 1.001f + 1e-3f : 1e30f;
+        const float t = logf(255.0f * op);
+        if (t > 0.f) ey = 2.0f * (t + 1e-4f) * 1.002f;
         if (!(ey == ey)) ey = 1e30f;
     }
     float4* rec = reinterpret_cast<float4*>(a.g_rec + (size_t)idx * a.rec);

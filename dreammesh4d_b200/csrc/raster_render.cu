@@ -79,7 +79,7 @@ __device__ __forceinline__ void load_features(const float4* r, float (&f)[C], fl
 // ------------------------------------------------------------------------------------------------
 // Each warp owns two pixel rows of the tile (16 x 2).  For every group of 32 staged instances the
 // lanes test the instances' row masks against the warp's rows and ballot: the warp then walks only
-// the set bits, i.e. only instances that can reach alpha >= 1/255 somewhere in its two rows.
+// the set bits, i.e. only instances that can reach alpha >= 1/255 somewhere in its 16x2 strip.
 template <int C>
 __global__ void __launch_bounds__(CHUNK) render_forward_kernel(RasterLayout L, const float* __restrict__ view_params,
                                                                 float* __restrict__ out_color,
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(CHUNK) render_forward_kernel(RasterLayout L, c
     const int px = tile_x * DM4D_TILE + (tid & 15), py = tile_y * DM4D_TILE + (tid >> 4);
     const bool inside = px < L.W && py < L.H;
     const float pfx = (float)px, pfy = (float)py;
-    const unsigned int my_rows = 3u << (2 * (tid >> 5));
+    const unsigned int my_rows = 1u << (tid >> 5);     // this warp's strip bit
 
     const unsigned int beg = L.tile_offset[gt];
     const int n = L.hdr->overflow ? 0 : (int)(L.tile_offset[gt + 1] - beg);
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(CHUNK) render_backward_kernel(RasterLayout L, 
     const float pfx = (float)px, pfy = (float)py;
     const size_t npix = (size_t)L.H * L.W;
     const size_t pix = (size_t)py * L.W + px;
-    const unsigned int my_rows = 3u << (2 * (tid >> 5));
+    const unsigned int my_rows = 1u << (tid >> 5);     // this warp's strip bit
 
     const unsigned int beg = L.tile_offset[gt];
     const int n = L.hdr->overflow ? 0 : (int)(L.tile_offset[gt + 1] - beg);
