@@ -6,20 +6,23 @@
 // and alpha outputs.  One CTA per (view, tile), one thread per pixel, all views in one launch.
 //
 // B200 design: the depth-sorted instances of a tile are a contiguous run of packed 48/64-byte
-// records (written by sort_pack_kernel), so one elected thread streams them into a multi-stage
-// shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) while the 8 warps
-// composite the previous chunk; no per-thread gather, no register staging.  The backward walks
-// the same stream back to front, reduces the per-pixel partial gradients across the warp with
-// shuffles (only for warps that have a contributing lane), accumulates them per instance in
-// shared memory and flushes one vectorised atomic row per (instance, tile) instead of upstream's
-// ten global atomics per (pixel, instance).
+// records (written by sort_pack_kernel).  Every WARP owns a 16x2 pixel strip and streams the tile's
+// records through its own small shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier
+// complete_tx, issued by the warp's lane 0): warps never meet at a block barrier, so a warp whose strip
+// is light (or saturated) runs ahead / retires while its neighbours keep compositing.  Per group of
+// 32 staged instances the lanes ballot the instances' strip masks and the warp walks only instances
+// that can reach its strip.  The backward walks the same stream back to front, reduces the per-pixel
+// partial gradients across the warp with a 16-shuffle recursive-halving reduction (only when a lane
+// contributes) and issues ONE coalesced 12/16-lane global reduction (RED.ADD.F32) per (warp, instance)
+// instead of upstream's ten global atomics per (pixel, instance).
 #include "raster_internal.cuh"
 
 namespace {
 
-constexpr int CHUNK = 256;       // instances per shared-memory stage
-constexpr int FWD_STAGES = 3;
-constexpr int BWD_STAGES = 2;
+constexpr int THREADS = 256;     // one thread per pixel of a 16x16 tile, 8 warps = 8 strips of 16x2
+constexpr int WARPS = THREADS / 32;
+constexpr int WCHUNK = 64;       // instances per per-warp stage
+constexpr int WSTAGES = 2;       // per-warp ring depth
 constexpr int FWD_UNROLL = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,50 +77,64 @@ __device__ __forceinline__ void load_features(const float4* r, float (&f)[C], fl
     }
 }
 
+// Per-warp streaming ring -------------------------------------------------------------------------
+template <int C>
+struct WarpRing {
+    using TR = RecTraits<C>;
+    float4* buf;        // [WSTAGES][WCHUNK * R4]
+    uint64_t* full;     // [WSTAGES]
+    const float* stream;
+    int n;              // instances available in the tile
+    __device__ __forceinline__ void init(unsigned char* smem_raw, int warp, int lane, const float* stream_, int n_) {
+        buf = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * WSTAGES * WCHUNK * TR::R4;
+        full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * WSTAGES * WCHUNK * TR::REC * sizeof(float)) + warp * WSTAGES;
+        stream = stream_;
+        n = n_;
+        if (lane == 0) {
+            for (int s = 0; s < WSTAGES; ++s) mbar_init(&full[s], 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+    }
+    // lane 0 only: stage chunk `c` (instances [c*WCHUNK, ...)) into slot `slot`
+    __device__ __forceinline__ void issue(int c, int slot) {
+        const int cnt = min(WCHUNK, n - c * WCHUNK);
+        const uint32_t bytes = (uint32_t)cnt * TR::REC * sizeof(float);
+        mbar_expect_tx(&full[slot], bytes);
+        bulk_g2s(buf + (size_t)slot * WCHUNK * TR::R4, stream + (size_t)c * WCHUNK * TR::REC, bytes, &full[slot]);
+    }
+    __device__ __forceinline__ const float4* wait(int slot, int use) {
+        mbar_wait(&full[slot], (uint32_t)use & 1u);
+        return buf + (size_t)slot * WCHUNK * TR::R4;
+    }
+    static constexpr size_t smem_bytes() {
+        return (size_t)WARPS * WSTAGES * WCHUNK * TR::REC * sizeof(float) + (size_t)WARPS * WSTAGES * sizeof(uint64_t);
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-// Each warp owns two pixel rows of the tile (16 x 2).  For every group of 32 staged instances the
-// lanes test the instances' row masks against the warp's rows and ballot: the warp then walks only
-// the set bits, i.e. only instances that can reach alpha >= 1/255 somewhere in its 16x2 strip.
 template <int C>
-__global__ void __launch_bounds__(CHUNK) render_forward_kernel(RasterLayout L, const float* __restrict__ view_params,
-                                                                float* __restrict__ out_color,
-                                                                float* __restrict__ out_depth,
-                                                                float* __restrict__ out_alpha) {
+__global__ void __launch_bounds__(THREADS) render_forward_kernel(RasterLayout L, const float* __restrict__ view_params,
+                                                                  float* __restrict__ out_color,
+                                                                  float* __restrict__ out_depth,
+                                                                  float* __restrict__ out_alpha) {
     using TR = RecTraits<C>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* buf = reinterpret_cast<float4*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)FWD_STAGES * CHUNK * TR::REC * sizeof(float));
 
     const int gt = (int)L.tile_order[blockIdx.x];
     const int v = gt / L.tiles, t = gt - v * L.tiles;
     const int tile_x = t % L.gx, tile_y = t / L.gx;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int px = tile_x * DM4D_TILE + (tid & 15), py = tile_y * DM4D_TILE + (tid >> 4);
     const bool inside = px < L.W && py < L.H;
     const float pfx = (float)px, pfy = (float)py;
-    const unsigned int my_rows = 1u << (tid >> 5);     // this warp's strip bit
+    const unsigned int my_strip = 1u << warp;
 
     const unsigned int beg = L.tile_offset[gt];
     const int n = L.hdr->overflow ? 0 : (int)(L.tile_offset[gt + 1] - beg);
-    const int nchunks = (n + CHUNK - 1) / CHUNK;
-    const float* stream = L.stream + (size_t)beg * TR::REC;
-
-    if (tid == 0) {
-        for (int s = 0; s < FWD_STAGES; ++s) mbar_init(&full[s], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    auto issue = [&](int c) {
-        const int s = c % FWD_STAGES;
-        const int cnt = min(CHUNK, n - c * CHUNK);
-        const uint32_t bytes = (uint32_t)cnt * TR::REC * sizeof(float);
-        mbar_expect_tx(&full[s], bytes);
-        bulk_g2s(buf + (size_t)s * CHUNK * TR::R4, stream + (size_t)c * CHUNK * TR::REC, bytes, &full[s]);
-    };
-    if (tid == 0)
-        for (int c = 0; c < min(FWD_STAGES, nchunks); ++c) issue(c);
+    const int nchunks = (n + WCHUNK - 1) / WCHUNK;
 
     bool done = !inside;
     bool warp_done = __all_sync(0xffffffffu, done);
@@ -127,67 +144,71 @@ __global__ void __launch_bounds__(CHUNK) render_forward_kernel(RasterLayout L, c
     for (int ch = 0; ch < C; ++ch) Cacc[ch] = 0.f;
     unsigned int last = 0;
 
-    int c = 0;
-    for (; c < nchunks; ++c) {
-        const int s = c % FWD_STAGES;
-        mbar_wait(&full[s], (uint32_t)(c / FWD_STAGES) & 1u);
-        const int cnt = min(CHUNK, n - c * CHUNK);
-        const float4* r = buf + (size_t)s * CHUNK * TR::R4;
-        for (int g0 = 0; g0 < cnt && !warp_done; g0 += 32) {
-            const int jj = g0 + lane;
-            const unsigned int m = jj < cnt ? __float_as_uint(r[jj * TR::R4 + 1].z) : 0u;
-            unsigned int bal = __ballot_sync(0xffffffffu, (m & my_rows) != 0u);
-            while (bal) {
-                // Take up to FWD_UNROLL candidates at once: their loads, power and exp are independent, only
-                // the blend below is sequential, so a lone warp (the tail of a heavy tile) is not latency-bound.
-                int js[FWD_UNROLL];
-                float al[FWD_UNROLL];
+    if (!warp_done && nchunks > 0) {
+        WarpRing<C> ring;
+        ring.init(smem_raw, warp, lane, L.stream + (size_t)beg * TR::REC, n);
+        if (lane == 0)
+            for (int c = 0; c < min(WSTAGES, nchunks); ++c) ring.issue(c, c);
+        int c = 0;
+        for (; c < nchunks; ++c) {
+            const int slot = c % WSTAGES;
+            const float4* r = ring.wait(slot, c / WSTAGES);
+            const int cnt = min(WCHUNK, n - c * WCHUNK);
+            for (int g0 = 0; g0 < cnt && !warp_done; g0 += 32) {
+                const int jj = g0 + lane;
+                const unsigned int m = jj < cnt ? __float_as_uint(r[jj * TR::R4 + 1].z) : 0u;
+                unsigned int bal = __ballot_sync(0xffffffffu, (m & my_strip) != 0u);
+                while (bal) {
+                    // Take up to FWD_UNROLL candidates at once: their loads, power and exp are independent,
+                    // only the blend below is sequential.
+                    int js[FWD_UNROLL];
+                    float al[FWD_UNROLL];
 #pragma unroll
-                for (int u = 0; u < FWD_UNROLL; ++u) {
-                    js[u] = bal ? g0 + __ffs(bal) - 1 : -1;
-                    bal &= bal - 1;
-                }
+                    for (int u = 0; u < FWD_UNROLL; ++u) {
+                        js[u] = bal ? g0 + __ffs(bal) - 1 : -1;
+                        bal &= bal - 1;
+                    }
 #pragma unroll
-                for (int u = 0; u < FWD_UNROLL; ++u) {
-                    al[u] = 0.f;
-                    if (js[u] >= 0 && !done) {
-                        const float4* rp = r + js[u] * TR::R4;
-                        const float4 a = rp[0];
-                        const float4 b = rp[1];
-                        const float dx = a.x - pfx, dy = a.y - pfy;
-                        const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-                        const float alpha = fminf(0.99f, b.y * expf(power));
-                        al[u] = (power > 0.0f || alpha < 1.0f / 255.0f) ? 0.f : alpha;
+                    for (int u = 0; u < FWD_UNROLL; ++u) {
+                        al[u] = 0.f;
+                        if (js[u] >= 0 && !done) {
+                            const float4* rp = r + js[u] * TR::R4;
+                            const float4 a = rp[0];
+                            const float4 b = rp[1];
+                            const float dx = a.x - pfx, dy = a.y - pfy;
+                            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+                            const float alpha = fminf(0.99f, b.y * expf(power));
+                            al[u] = (power > 0.0f || alpha < 1.0f / 255.0f) ? 0.f : alpha;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < FWD_UNROLL; ++u) {
+                        if (al[u] > 0.f && !done) {
+                            const float alpha = al[u];
+                            const float test_T = T * (1.0f - alpha);
+                            if (test_T < 0.0001f) { done = true; continue; }
+                            float f[C], dep;
+                            load_features<C>(r + js[u] * TR::R4, f, dep);
+                            const float w = alpha * T;
+#pragma unroll
+                            for (int ch = 0; ch < C; ++ch) Cacc[ch] += f[ch] * w;
+                            D += dep * w;
+                            Wg += w;
+                            T = test_T;
+                            last = (unsigned int)(c * WCHUNK + js[u] + 1);
+                        }
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < FWD_UNROLL; ++u) {
-                    if (al[u] > 0.f && !done) {
-                        const float alpha = al[u];
-                        const float test_T = T * (1.0f - alpha);
-                        if (test_T < 0.0001f) { done = true; continue; }
-                        float f[C], dep;
-                        load_features<C>(r + js[u] * TR::R4, f, dep);
-                        const float w = alpha * T;
-#pragma unroll
-                        for (int ch = 0; ch < C; ++ch) Cacc[ch] += f[ch] * w;
-                        D += dep * w;
-                        Wg += w;
-                        T = test_T;
-                        last = (unsigned int)(c * CHUNK + js[u] + 1);
-                    }
-                }
+                warp_done = __all_sync(0xffffffffu, done);
             }
-            warp_done = __all_sync(0xffffffffu, done);
+            __syncwarp();
+            if (warp_done) break;
+            if (lane == 0 && c + WSTAGES < nchunks) ring.issue(c + WSTAGES, slot);
         }
-        const int ndone = __syncthreads_count(done ? 1 : 0);
-        if (ndone == CHUNK) break;
-        if (tid == 0 && c + FWD_STAGES < nchunks) issue(c + FWD_STAGES);
+        // drain bulk copies still in flight before this warp (and eventually the CTA's shared memory) retires
+        if (c < nchunks)
+            for (int c2 = c + 1; c2 < min(nchunks, c + WSTAGES); ++c2) ring.wait(c2 % WSTAGES, c2 / WSTAGES);
     }
-    // drain bulk copies that are still in flight before the CTA (and its shared memory) retires
-    if (tid == 0 && c < nchunks)
-        for (int c2 = c + 1; c2 < min(nchunks, c + FWD_STAGES); ++c2)
-            mbar_wait(&full[c2 % FWD_STAGES], (uint32_t)(c2 / FWD_STAGES) & 1u);
 
     if (inside) {
         const float* bg = view_params + (size_t)v * DM4D_VIEW_STRIDE + DM4D_VIEW_BG;
@@ -230,61 +251,42 @@ __device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane)
 }
 
 template <int C>
-__global__ void __launch_bounds__(CHUNK) render_backward_kernel(RasterLayout L, const float* __restrict__ view_params,
-                                                                 const float* __restrict__ out_alpha,
-                                                                 const float* __restrict__ dL_dcolor,
-                                                                 const float* __restrict__ dL_ddepth,
-                                                                 const float* __restrict__ dL_dalpha_img) {
+__global__ void __launch_bounds__(THREADS) render_backward_kernel(RasterLayout L, const float* __restrict__ view_params,
+                                                                   const float* __restrict__ out_alpha,
+                                                                   const float* __restrict__ dL_dcolor,
+                                                                   const float* __restrict__ dL_ddepth,
+                                                                   const float* __restrict__ dL_dalpha_img) {
     using TR = RecTraits<C>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* buf = reinterpret_cast<float4*>(smem_raw);
-    float* sacc = reinterpret_cast<float*>(smem_raw + (size_t)BWD_STAGES * CHUNK * TR::REC * sizeof(float));
-    uint64_t* full = reinterpret_cast<uint64_t*>(sacc + (size_t)CHUNK * TR::ACC);
-    __shared__ unsigned int s_max_contrib;
 
     const int gt = (int)L.tile_order[blockIdx.x];
     const int v = gt / L.tiles, t = gt - v * L.tiles;
     const int tile_x = t % L.gx, tile_y = t / L.gx;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int px = tile_x * DM4D_TILE + (tid & 15), py = tile_y * DM4D_TILE + (tid >> 4);
     const bool inside = px < L.W && py < L.H;
     const float pfx = (float)px, pfy = (float)py;
     const size_t npix = (size_t)L.H * L.W;
     const size_t pix = (size_t)py * L.W + px;
-    const unsigned int my_rows = 1u << (tid >> 5);     // this warp's strip bit
+    const unsigned int my_strip = 1u << warp;
 
     const unsigned int beg = L.tile_offset[gt];
     const int n = L.hdr->overflow ? 0 : (int)(L.tile_offset[gt + 1] - beg);
     if (n == 0) return;
-    const float* stream = L.stream + (size_t)beg * TR::REC;
 
     const unsigned int last_contributor = inside ? L.n_contrib[(size_t)v * npix + pix] : 0u;
-    if (tid == 0) {
-        s_max_contrib = 0u;
-        for (int s = 0; s < BWD_STAGES; ++s) mbar_init(&full[s], 1);
-        fence_mbar_init();
-    }
-    for (int i = tid; i < CHUNK * TR::ACC; i += CHUNK) sacc[i] = 0.f;
-    __syncthreads();
     unsigned int warp_last = last_contributor;      // last contributor over the warp's 32 pixels
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
-    if (lane == 0 && warp_last > 0) atomicMax(&s_max_contrib, warp_last);
-    __syncthreads();
-    const int max_contrib = (int)s_max_contrib;
-    if (max_contrib == 0) return;
-    const int nchunks = (max_contrib + CHUNK - 1) / CHUNK;   // chunks that hold at least one contributor
+    if (warp_last == 0) return;                      // nothing composited in this strip
+    const int nlive = min(n, (int)warp_last);        // this warp only needs instances in front of its last contributor
+    const int nchunks = (nlive + WCHUNK - 1) / WCHUNK;
 
-    auto issue = [&](int k) {   // k-th chunk in processing order = chunk index nchunks-1-k
-        const int c = nchunks - 1 - k;
-        const int s = k % BWD_STAGES;
-        const int cnt = min(CHUNK, n - c * CHUNK);
-        const uint32_t bytes = (uint32_t)cnt * TR::REC * sizeof(float);
-        mbar_expect_tx(&full[s], bytes);
-        bulk_g2s(buf + (size_t)s * CHUNK * TR::R4, stream + (size_t)c * CHUNK * TR::REC, bytes, &full[s]);
-    };
-    if (tid == 0)
-        for (int k = 0; k < min(BWD_STAGES, nchunks); ++k) issue(k);
+    WarpRing<C> ring;
+    ring.init(smem_raw, warp, lane, L.stream + (size_t)beg * TR::REC, nlive);
+    // k-th chunk in processing order = chunk index nchunks-1-k (back to front)
+    if (lane == 0)
+        for (int k = 0; k < min(WSTAGES, nchunks); ++k) ring.issue(nchunks - 1 - k, k);
 
     const float* vp = view_params + (size_t)v * DM4D_VIEW_STRIDE;
     float gC[C];
@@ -303,24 +305,24 @@ __global__ void __launch_bounds__(CHUNK) render_backward_kernel(RasterLayout L, 
     for (int ch = 0; ch < C; ++ch) { accum_rec[ch] = 0.f; last_color[ch] = 0.f; }
     float accum_d = 0.f, last_depth = 0.f, accum_a = 0.f, last_alpha = 0.f;
     const float ddelx_dx = 0.5f * (float)L.W, ddely_dy = 0.5f * (float)L.H;
+    float* accum_view = L.accum + (size_t)v * L.P * TR::ACC;
+    const int slot = lane >> 1;
+    const bool writer = !(lane & 1) && slot < TR::ACC && slot != 7;
 
     for (int k = 0; k < nchunks; ++k) {
         const int c = nchunks - 1 - k;
-        const int s = k % BWD_STAGES;
-        mbar_wait(&full[s], (uint32_t)(k / BWD_STAGES) & 1u);
-        const int cnt = min(CHUNK, n - c * CHUNK);
-        const float4* r = buf + (size_t)s * CHUNK * TR::R4;
-        // this warp only needs instances in front of its own last contributor
-        const int wcnt = min(cnt, (int)warp_last - c * CHUNK);
-        for (int g0 = wcnt > 0 ? ((wcnt - 1) & ~31) : -1; g0 >= 0; g0 -= 32) {
+        const int sl = k % WSTAGES;
+        const float4* r = ring.wait(sl, k / WSTAGES);
+        const int cnt = min(WCHUNK, nlive - c * WCHUNK);
+        for (int g0 = (cnt - 1) & ~31; g0 >= 0; g0 -= 32) {
             const int jj = g0 + lane;
-            const unsigned int m = jj < wcnt ? __float_as_uint(r[jj * TR::R4 + 1].z) : 0u;
-            unsigned int bal = __ballot_sync(0xffffffffu, (m & my_rows) != 0u);
+            const unsigned int m = jj < cnt ? __float_as_uint(r[jj * TR::R4 + 1].z) : 0u;
+            unsigned int bal = __ballot_sync(0xffffffffu, (m & my_strip) != 0u);
             while (bal) {
                 const int bpos = 31 - __clz(bal);
                 bal &= ~(1u << bpos);
                 const int j = g0 + bpos;
-                const unsigned int gi = (unsigned int)(c * CHUNK + j);
+                const unsigned int gi = (unsigned int)(c * WCHUNK + j);
                 const float4* rp = r + j * TR::R4;
                 bool valid = gi < last_contributor;
                 float4 a, b;
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(CHUNK) render_backward_kernel(RasterLayout L, 
                 }
                 if (!__any_sync(0xffffffffu, valid)) continue;
 
-                // slots: 0-1 dmean2D, 2-4 dconic, 5 dopacity, 6 ddepth, 7 #contributing pixels, 8.. dfeatures
+                // slots: 0-1 dmean2D, 2-4 dconic, 5 dopacity, 6 ddepth, 7 unused, 8.. dfeatures
                 float gv[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) gv[i] = 0.f;
@@ -375,39 +377,22 @@ __global__ void __launch_bounds__(CHUNK) render_backward_kernel(RasterLayout L, 
                     gv[3] = -0.5f * gdx * dy * dL_dG;
                     gv[4] = -0.5f * gdy * dy * dL_dG;
                     gv[5] = G * dL_dalpha;
-                    gv[7] = 1.0f;
                 }
                 const float tot = warp_reduce_scatter16(gv, lane);
-                const int slot = lane >> 1;
-                if (!(lane & 1) && slot < TR::ACC) atomicAdd(sacc + (size_t)j * TR::ACC + slot, tot);
+                // one coalesced reduction per (warp, instance): lanes 0,2,4,.. add slot 0,1,2,.. of the instance's row
+                const int id = __float_as_int(rp[1].w);
+                if (writer) atomicAdd(accum_view + (size_t)id * TR::ACC + slot, tot);
             }
         }
-        __syncthreads();
-        // flush this chunk's per-instance sums: one vectorised atomic row per touched instance
-        if (tid < cnt) {
-            float4* row = reinterpret_cast<float4*>(sacc + (size_t)tid * TR::ACC);
-            const float4 r0 = row[0], r1 = row[1];
-            if (r1.w != 0.f) {
-                const int id = __float_as_int(r[tid * TR::R4 + 1].w);
-                float4* dst = reinterpret_cast<float4*>(L.accum + ((size_t)v * L.P + id) * TR::ACC);
-                atomicAdd(dst + 0, r0);
-                atomicAdd(dst + 1, make_float4(r1.x, r1.y, r1.z, 0.f));
-#pragma unroll
-                for (int q = 2; q < TR::ACC / 4; ++q) atomicAdd(dst + q, row[q]);
-#pragma unroll
-                for (int q = 0; q < TR::ACC / 4; ++q) row[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        __syncthreads();
-        if (tid == 0 && k + BWD_STAGES < nchunks) issue(k + BWD_STAGES);
+        __syncwarp();
+        if (lane == 0 && k + WSTAGES < nchunks) ring.issue(nchunks - 1 - (k + WSTAGES), sl);
     }
 }
 
 template <int C>
 int launch_fwd_t(const dm4d_raster_desc* d, const RasterLayout& L, float* out_color, float* out_depth,
                  float* out_alpha, cudaStream_t s) {
-    using TR = RecTraits<C>;
-    const size_t smem = (size_t)FWD_STAGES * CHUNK * TR::REC * sizeof(float) + FWD_STAGES * sizeof(uint64_t);
+    const size_t smem = WarpRing<C>::smem_bytes();
     static bool configured = false;
     if (!configured) {
         DM4D_CUDA_CHECK(cudaFuncSetAttribute(render_forward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -415,8 +400,8 @@ int launch_fwd_t(const dm4d_raster_desc* d, const RasterLayout& L, float* out_co
     }
     {
         KernelTimer kt(DM4D_K_RENDER_FWD, s);
-        render_forward_kernel<C><<<(unsigned)(L.n_views * L.tiles), CHUNK, smem, s>>>(L, d->view_params, out_color,
-                                                                                      out_depth, out_alpha);
+        render_forward_kernel<C><<<(unsigned)(L.n_views * L.tiles), THREADS, smem, s>>>(L, d->view_params, out_color,
+                                                                                        out_depth, out_alpha);
     }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
@@ -425,9 +410,7 @@ int launch_fwd_t(const dm4d_raster_desc* d, const RasterLayout& L, float* out_co
 template <int C>
 int launch_bwd_t(const dm4d_raster_desc* d, const RasterLayout& L, const float* out_alpha, const float* dL_dcolor,
                  const float* dL_ddepth, const float* dL_dalpha, cudaStream_t s) {
-    using TR = RecTraits<C>;
-    const size_t smem = (size_t)BWD_STAGES * CHUNK * TR::REC * sizeof(float) + (size_t)CHUNK * TR::ACC * sizeof(float) +
-                        BWD_STAGES * sizeof(uint64_t);
+    const size_t smem = WarpRing<C>::smem_bytes();
     static bool configured = false;
     if (!configured) {
         DM4D_CUDA_CHECK(cudaFuncSetAttribute(render_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -436,8 +419,8 @@ int launch_bwd_t(const dm4d_raster_desc* d, const RasterLayout& L, const float* 
     DM4D_CUDA_CHECK(cudaMemsetAsync(L.accum, 0, (size_t)L.n_views * L.P * L.acc * sizeof(float), s));
     {
         KernelTimer kt(DM4D_K_RENDER_BWD, s);
-        render_backward_kernel<C><<<(unsigned)(L.n_views * L.tiles), CHUNK, smem, s>>>(L, d->view_params, out_alpha,
-                                                                                       dL_dcolor, dL_ddepth, dL_dalpha);
+        render_backward_kernel<C><<<(unsigned)(L.n_views * L.tiles), THREADS, smem, s>>>(L, d->view_params, out_alpha,
+                                                                                         dL_dcolor, dL_ddepth, dL_dalpha);
     }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
