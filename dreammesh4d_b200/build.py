@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(src: Path) -> Path:
         obj = objdir / (src.stem + ".o")
-        cmd = [nvcc, *ARCH, *COMMON, *UNITS[src.name], "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *ARCH, *COMMON, *UNITS[src.name], *os.environ.get("DM4D_NVCC_EXTRA", "").split(), "-c", str(src), "-o", str(obj)]
         if host_cc:
             cmd[1:1] = ["-ccbin", host_cc]
         if verbose:

@@ -21,8 +21,17 @@ namespace {
 
 constexpr int THREADS = 256;     // one thread per pixel of a 16x16 tile, 8 warps = 8 strips of 16x2
 constexpr int WARPS = THREADS / 32;
-constexpr int WCHUNK = 64;       // instances per per-warp stage
-constexpr int WSTAGES = 2;       // per-warp ring depth
+#ifndef DM4D_WCHUNK
+#define DM4D_WCHUNK 64
+#endif
+#ifndef DM4D_WSTAGES
+#define DM4D_WSTAGES 2
+#endif
+#ifndef DM4D_BWD_MIN_BLOCKS
+#define DM4D_BWD_MIN_BLOCKS 4
+#endif
+constexpr int WCHUNK = DM4D_WCHUNK;     // instances per per-warp stage
+constexpr int WSTAGES = DM4D_WSTAGES;   // per-warp ring depth
 constexpr int FWD_UNROLL = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -251,7 +260,7 @@ __device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane)
 }
 
 template <int C>
-__global__ void __launch_bounds__(THREADS) render_backward_kernel(RasterLayout L, const float* __restrict__ view_params,
+__global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_kernel(RasterLayout L, const float* __restrict__ view_params,
                                                                    const float* __restrict__ out_alpha,
                                                                    const float* __restrict__ dL_dcolor,
                                                                    const float* __restrict__ dL_ddepth,
@@ -346,7 +355,8 @@ __global__ void __launch_bounds__(THREADS) render_backward_kernel(RasterLayout L
 #pragma unroll
                 for (int i = 0; i < 16; ++i) gv[i] = 0.f;
                 if (valid) {
-                    T = T / (1.0f - alpha);
+                    const float inv_1ma = __frcp_rn(1.0f - alpha);     // shared by both uses below (1 ulp)
+                    T = T * inv_1ma;
                     const float w = alpha * T;
                     float f[C], dep;
                     load_features<C>(rp, f, dep);
@@ -366,7 +376,7 @@ __global__ void __launch_bounds__(THREADS) render_backward_kernel(RasterLayout L
                     dL_dalpha += (1.f - accum_a) * gA;
                     dL_dalpha *= T;
                     last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                    dL_dalpha += (-T_final * inv_1ma) * bg_dot;
                     const float dL_dG = b.y * dL_dalpha;
                     const float gdx = G * dx, gdy = G * dy;
                     const float dG_ddelx = -gdx * a.z - gdy * a.w;
