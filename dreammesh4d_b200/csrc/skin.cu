@@ -419,6 +419,98 @@ __global__ void __launch_bounds__(DM4D_BLOCK) sugar_rest_frames_kernel(const flo
     }
 }
 
+// Backward of sugar_rest_frames_kernel: exact Euclidean gradient of (quaternions, normals) w.r.t. the mesh
+// vertices and the per-Gaussian complex in-plane rotation (needed in the static stage, where both are learnable:
+// sugar.py:333-376).  The quaternion branch chosen by matrix_to_quaternion is treated as locally constant.
+__global__ void __launch_bounds__(DM4D_BLOCK) sugar_rest_frames_backward_kernel(const float* verts, const int32_t* faces,
+                                                                                const float* complex_rot, int F, int g,
+                                                                                const float* g_quats, const float* g_normals,
+                                                                                float* dverts, float* dcomplex) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int i0 = faces[f * 3], i1 = faces[f * 3 + 1], i2 = faces[f * 3 + 2];
+    const f3 x0 = ld3(verts + (size_t)i0 * 3), x1 = ld3(verts + (size_t)i1 * 3), x2 = ld3(verts + (size_t)i2 * 3);
+    const f3 e1 = x1 - x0, e2 = x2 - x0;
+    const f3 c = cross(e1, e2);
+    const float len = sqrtf(dot(c, c));
+    const float lenc = fmaxf(len, 1e-6f);
+    f3 R0 = (1.f / lenc) * c;
+    R0 = normalize12(R0);
+    const f3 d = x0 - x1;
+    const float dl = fmaxf(sqrtf(dot(d, d)), 1e-12f);
+    const f3 b1 = (1.f / dl) * d;
+    const f3 p = cross(R0, b1);
+    const float pl = fmaxf(sqrtf(dot(p, p)), 1e-12f);
+    const f3 b2 = (1.f / pl) * p;
+
+    f3 dR0 = mk3(0, 0, 0), db1 = mk3(0, 0, 0), db2 = mk3(0, 0, 0);
+    for (int j = 0; j < g; ++j) {
+        const size_t gi = (size_t)f * g + j;
+        if (g_normals) dR0 = dR0 + ld3(g_normals + gi * 3);
+        if (!g_quats) { if (dcomplex) { dcomplex[gi * 2] = 0.f; dcomplex[gi * 2 + 1] = 0.f; } continue; }
+        const float cr0 = complex_rot[gi * 2], ci0 = complex_rot[gi * 2 + 1];
+        const float sn = fmaxf(sqrtf(cr0 * cr0 + ci0 * ci0), 1e-12f);
+        const float cr = cr0 / sn, ci = ci0 / sn;
+        const f3 R1 = cr * b1 + ci * b2;
+        const f3 R2 = (-ci) * b1 + cr * b2;
+        const float m[3][3] = {{R0.x, R1.x, R2.x}, {R0.y, R1.y, R2.y}, {R0.z, R1.z, R2.z}};
+        const float lin[4] = {1.f + m[0][0] + m[1][1] + m[2][2], 1.f + m[0][0] - m[1][1] - m[2][2],
+                              1.f - m[0][0] + m[1][1] - m[2][2], 1.f - m[0][0] - m[1][1] + m[2][2]};
+        float qa[4];
+        int best = 0;
+        for (int k = 0; k < 4; ++k) { qa[k] = sqrtf(fmaxf(0.f, lin[k])); if (qa[k] > qa[best]) best = k; }
+        float cand[4];
+        if (best == 0) { cand[0] = lin[0]; cand[1] = m[2][1] - m[1][2]; cand[2] = m[0][2] - m[2][0]; cand[3] = m[1][0] - m[0][1]; }
+        else if (best == 1) { cand[0] = m[2][1] - m[1][2]; cand[1] = lin[1]; cand[2] = m[1][0] + m[0][1]; cand[3] = m[0][2] + m[2][0]; }
+        else if (best == 2) { cand[0] = m[0][2] - m[2][0]; cand[1] = m[1][0] + m[0][1]; cand[2] = lin[2]; cand[3] = m[1][2] + m[2][1]; }
+        else { cand[0] = m[1][0] - m[0][1]; cand[1] = m[2][0] + m[0][2]; cand[2] = m[2][1] + m[1][2]; cand[3] = lin[3]; }
+        const float D = 2.f * fmaxf(qa[best], 0.1f);
+        float u[4], un = 0.f;
+        for (int k = 0; k < 4; ++k) { u[k] = cand[k] / D; un += u[k] * u[k]; }
+        un = fmaxf(sqrtf(un), 1e-12f);
+        const float4 gq = ldq(g_quats + gi * 4);
+        const float gqa[4] = {gq.x, gq.y, gq.z, gq.w};
+        float q[4], qg = 0.f;
+        for (int k = 0; k < 4; ++k) { q[k] = u[k] / un; qg += q[k] * gqa[k]; }
+        float du[4], dudotu = 0.f;
+        for (int k = 0; k < 4; ++k) { du[k] = (gqa[k] - q[k] * qg) / un; dudotu += du[k] * u[k]; }
+        float dcand[4];
+        for (int k = 0; k < 4; ++k) dcand[k] = du[k] / D;
+        float dlin = (qa[best] > 0.1f) ? (-(dudotu / D) * 2.f) / (2.f * qa[best]) : 0.f;   // through D = 2 sqrt(lin)
+        float dm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        if (best == 0) { dlin += dcand[0]; dm[2][1] += dcand[1]; dm[1][2] -= dcand[1]; dm[0][2] += dcand[2]; dm[2][0] -= dcand[2]; dm[1][0] += dcand[3]; dm[0][1] -= dcand[3]; }
+        else if (best == 1) { dm[2][1] += dcand[0]; dm[1][2] -= dcand[0]; dlin += dcand[1]; dm[1][0] += dcand[2]; dm[0][1] += dcand[2]; dm[0][2] += dcand[3]; dm[2][0] += dcand[3]; }
+        else if (best == 2) { dm[0][2] += dcand[0]; dm[2][0] -= dcand[0]; dm[1][0] += dcand[1]; dm[0][1] += dcand[1]; dlin += dcand[2]; dm[1][2] += dcand[3]; dm[2][1] += dcand[3]; }
+        else { dm[1][0] += dcand[0]; dm[0][1] -= dcand[0]; dm[2][0] += dcand[1]; dm[0][2] += dcand[1]; dm[2][1] += dcand[2]; dm[1][2] += dcand[2]; dlin += dcand[3]; }
+        const float sg[4][3] = {{1, 1, 1}, {1, -1, -1}, {-1, 1, -1}, {-1, -1, 1}};
+        for (int k = 0; k < 3; ++k) dm[k][k] += sg[best][k] * dlin;
+        const f3 gR0 = mk3(dm[0][0], dm[1][0], dm[2][0]), gR1 = mk3(dm[0][1], dm[1][1], dm[2][1]), gR2 = mk3(dm[0][2], dm[1][2], dm[2][2]);
+        dR0 = dR0 + gR0;
+        const float dcr = dot(gR1, b1) + dot(gR2, b2), dci = dot(gR1, b2) - dot(gR2, b1);
+        db1 = db1 + cr * gR1 - ci * gR2;
+        db2 = db2 + ci * gR1 + cr * gR2;
+        const float cd = cr * dcr + ci * dci;
+        dcomplex[gi * 2] = (dcr - cr * cd) / sn;
+        dcomplex[gi * 2 + 1] = (dci - ci * cd) / sn;
+    }
+    // b2 = p/|p|, p = R0 x b1
+    const f3 dp = (1.f / pl) * (db2 - dot(b2, db2) * b2);
+    dR0 = dR0 + cross(b1, dp);
+    db1 = db1 + cross(dp, R0);
+    // b1 = d/|d|, d = x0 - x1
+    const f3 dd = (1.f / dl) * (db1 - dot(b1, db1) * b1);
+    f3 dx0 = dd, dx1 = mk3(0, 0, 0) - dd, dx2 = mk3(0, 0, 0);
+    // R0 = c/|c|, c = e1 x e2
+    const f3 dc = len > 1e-6f ? (1.f / len) * (dR0 - dot(R0, dR0) * R0) : 1e6f * dR0;
+    const f3 de1 = cross(e2, dc), de2 = cross(dc, e1);
+    dx0 = dx0 - (de1 + de2);
+    dx1 = dx1 + de1;
+    dx2 = dx2 + de2;
+    atomicAdd(dverts + (size_t)i0 * 3 + 0, dx0.x); atomicAdd(dverts + (size_t)i0 * 3 + 1, dx0.y); atomicAdd(dverts + (size_t)i0 * 3 + 2, dx0.z);
+    atomicAdd(dverts + (size_t)i1 * 3 + 0, dx1.x); atomicAdd(dverts + (size_t)i1 * 3 + 1, dx1.y); atomicAdd(dverts + (size_t)i1 * 3 + 2, dx1.z);
+    atomicAdd(dverts + (size_t)i2 * 3 + 0, dx2.x); atomicAdd(dverts + (size_t)i2 * 3 + 1, dx2.y); atomicAdd(dverts + (size_t)i2 * 3 + 2, dx2.z);
+}
+
 int check_desc(const dm4d_skin_desc* d) {
     if (!d) { dm4d_set_error("skin desc is NULL"); return DM4D_EINVAL; }
     if (d->n_t <= 0 || d->V <= 0 || d->F <= 0 || d->M <= 0 || d->K <= 0 || d->g <= 0 || d->g > 6) {
@@ -499,6 +591,21 @@ extern "C" int dm4d_sugar_rest_frames(const float* verts, const int32_t* faces, 
     }
     cudaStream_t s = (cudaStream_t)stream;
     { KernelTimer kt(DM4D_K_REST_FRAMES, s); sugar_rest_frames_kernel<<<(unsigned)((F + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(verts, faces, complex_rot, F, g, quaternions, normals); }
+    DM4D_CUDA_CHECK(cudaGetLastError());
+    return DM4D_OK;
+}
+
+extern "C" int dm4d_sugar_rest_frames_backward(const float* verts, const int32_t* faces, const float* complex_rot,
+                                               int32_t V, int32_t F, int32_t g, const float* dL_dquaternions,
+                                               const float* dL_dnormals, float* dL_dverts, float* dL_dcomplex_rot,
+                                               void* stream) {
+    if (!verts || !faces || V <= 0 || F <= 0 || g <= 0 || g > 6 || !dL_dverts || (dL_dquaternions && (!complex_rot || !dL_dcomplex_rot))) {
+        dm4d_set_error("dm4d_sugar_rest_frames_backward: bad argument");
+        return DM4D_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    DM4D_CUDA_CHECK(cudaMemsetAsync(dL_dverts, 0, (size_t)V * 3 * sizeof(float), s));
+    { KernelTimer kt(DM4D_K_REST_FRAMES, s); sugar_rest_frames_backward_kernel<<<(unsigned)((F + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(verts, faces, complex_rot, F, g, dL_dquaternions, dL_dnormals, dL_dverts, dL_dcomplex_rot); }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }

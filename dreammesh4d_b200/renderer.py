@@ -44,6 +44,7 @@ class DiffGaussianBatchRenderer:
         self.training = training
         self.capacity = capacity          # None: exact sizing with one num_rendered read-back per batch
         self.last_state = None
+        self.last_view_params = None
 
     def batch_forward(self, batch: Dict[str, Any], compute_normal_from_dist: bool = True, node_attrs=None) -> Dict[str, Any]:
         geo = self.geometry
@@ -59,17 +60,29 @@ class DiffGaussianBatchRenderer:
             bg = 1.0 - bg                                                       # temporal.py:96-103
         bg6 = torch.cat([bg, bg]).expand(B, 6)                                  # the normal pass uses the same bg
 
-        timed = geo.deform(batch["timestamp"], node_attrs=node_attrs)           # one set per view
-        vp = R.make_view_params(view, proj, campos, tanx, tany, bg6, 1.0,
-                                set_index=torch.arange(B, device=dev))
+        static = "timestamp" not in batch       # static stage: diff_sugar_rasterizer_normal.py:79-226
         P = geo.n_gaussians
         screenspace = torch.zeros(B, P, 3, dtype=torch.float32, device=dev, requires_grad=True)   # temporal.py:108-113
         states = []
-        color6, radii, depth, alpha = R.rasterize_batch(
-            timed["means3D"], geo.get_opacity, geo.get_scaling, timed["rotations"], geo.get_points_rgb(), vp, H, W,
-            colors2=timed["normals"], means2D=screenspace, capacity=self.capacity, distinct_sets=True,
-            state_out=states)
+        if static:
+            # one shared attribute set for every view (SuGaRModel getters, sugar.py:528-546)
+            vp = R.make_view_params(view, proj, campos, tanx, tany, bg6, 1.0)
+            colors = batch.get("override_color", None)
+            if colors is None:
+                colors = geo.get_points_rgb()                                   # sugar_static.py:90-94 injects exactly this
+            color6, radii, depth, alpha = R.rasterize_batch(
+                geo.get_xyz, geo.get_opacity, geo.get_scaling, geo.get_rotation, colors, vp, H, W,
+                colors2=geo.get_gs_normals, means2D=screenspace, capacity=self.capacity, state_out=states)
+        else:
+            timed = geo.deform(batch["timestamp"], node_attrs=node_attrs)       # one set per view
+            vp = R.make_view_params(view, proj, campos, tanx, tany, bg6, 1.0,
+                                    set_index=torch.arange(B, device=dev))
+            color6, radii, depth, alpha = R.rasterize_batch(
+                timed["means3D"], geo.get_opacity, geo.get_scaling, timed["rotations"], geo.get_points_rgb(), vp, H, W,
+                colors2=timed["normals"], means2D=screenspace, capacity=self.capacity, distinct_sets=True,
+                state_out=states)
         self.last_state = states[0]
+        self.last_view_params = vp        # [B,48] camera block actually rasterized (include/dm4d.h layout)
         rgb, nrm = color6[:, :3], color6[:, 3:]
 
         mask = alpha > 0.99                                                     # temporal.py:180

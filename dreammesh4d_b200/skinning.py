@@ -101,22 +101,43 @@ def skin_gaussians(node_trans, node_rot, node_scale, node_opacity, rest_verts, f
                                bary, rest_quat, method, want_normals)
 
 
-def sugar_rest_frames(verts: torch.Tensor, faces: torch.Tensor, complex_rot: Optional[torch.Tensor], g: int,
-                      want_quaternions: bool = True, want_normals: bool = True):
-    """Rest-pose quaternions [P,4] (wxyz) and per-Gaussian face normals [P,3] (sugar.py:490-526). No autograd
-    (the static parameters are frozen in the dynamic stage, dynamic_sugar.py:79-87)."""
-    l = _lib.lib()
-    dev = verts.device
-    if dev.type != "cuda":
+class _RestFramesFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, complex_rot, faces, g):
+        l = _lib.lib()
+        dev = verts.device
+        v, c, f = _f32(verts), _f32(complex_rot), faces.contiguous()
+        P = f.shape[0] * g
+        q = torch.empty(P, 4, dtype=torch.float32, device=dev)
+        n = torch.empty(P, 3, dtype=torch.float32, device=dev)
+        check(l.dm4d_sugar_rest_frames(ptr(v), ptr(f), ptr(c), v.shape[0], f.shape[0], g, ptr(q), ptr(n),
+                                       torch.cuda.current_stream().cuda_stream), "dm4d_sugar_rest_frames")
+        ctx.keep, ctx.g = (v, c, f), g
+        return q, n
+
+    @staticmethod
+    def backward(ctx, g_q, g_n):
+        l = _lib.lib()
+        v, c, f = ctx.keep
+        gq = None if g_q is None else g_q.contiguous().float()
+        gn = None if g_n is None else g_n.contiguous().float()
+        dv = torch.empty_like(v)
+        dc = torch.empty_like(c)
+        check(l.dm4d_sugar_rest_frames_backward(ptr(v), ptr(f), ptr(c), v.shape[0], f.shape[0], ctx.g, ptr(gq), ptr(gn),
+                                                ptr(dv), ptr(dc), torch.cuda.current_stream().cuda_stream),
+              "dm4d_sugar_rest_frames_backward")
+        if gq is None:
+            dc.zero_()
+        return dv, dc, None, None
+
+
+def sugar_rest_frames(verts: torch.Tensor, faces: torch.Tensor, complex_rot: torch.Tensor, g: int):
+    """Rest-pose quaternions [P,4] (wxyz, normalised) and per-Gaussian unit face normals [P,3]
+    (SuGaRModel.quaternions / get_gs_normals, sugar.py:490-526).  Differentiable w.r.t. ``verts`` and
+    ``complex_rot`` (static stage); the static parameters are frozen in the dynamic stage
+    (dynamic_sugar.py:79-87) and then no backward is ever launched."""
+    if verts.device.type != "cuda":
         raise _lib.Dm4dError("dreammesh4d_b200 needs CUDA tensors (there is no CPU path)")
-    v = _f32(verts)
-    f = faces.contiguous()
-    if f.dtype != torch.int32:
+    if faces.dtype != torch.int32:
         raise TypeError("faces must be int32")
-    c = None if complex_rot is None else _f32(complex_rot)
-    P = f.shape[0] * g
-    q = torch.empty(P, 4, dtype=torch.float32, device=dev) if want_quaternions else None
-    n = torch.empty(P, 3, dtype=torch.float32, device=dev) if want_normals else None
-    check(l.dm4d_sugar_rest_frames(ptr(v), ptr(f), ptr(c), v.shape[0], f.shape[0], g, ptr(q), ptr(n),
-                                   torch.cuda.current_stream().cuda_stream), "dm4d_sugar_rest_frames")
-    return q, n
+    return _RestFramesFunction.apply(verts, complex_rot, faces, g)

@@ -174,6 +174,13 @@ int dm4d_skin_backward(const dm4d_skin_desc* d, const float* verts, const float*
 int dm4d_sugar_rest_frames(const float* verts, const int32_t* faces, const float* complex_rot, int32_t V,
                            int32_t F, int32_t g, float* quaternions, float* normals, void* stream);
 
+/* Backward of dm4d_sugar_rest_frames (static stage: vertices and in-plane rotations are learnable,
+ * sugar.py:333-376).  dL_dquaternions [P,4] / dL_dnormals [P,3] may be NULL.  Outputs (overwritten):
+ * dL_dverts [V,3], dL_dcomplex_rot [P,2] (required when dL_dquaternions is given). */
+int dm4d_sugar_rest_frames_backward(const float* verts, const int32_t* faces, const float* complex_rot, int32_t V,
+                                    int32_t F, int32_t g, const float* dL_dquaternions, const float* dL_dnormals,
+                                    float* dL_dverts, float* dL_dcomplex_rot, void* stream);
+
 /* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel launch).
  * Kernel ids: see DM4D_K_* below.  dm4d_profile_collect synchronises the recorded events, ADDS the
  * elapsed milliseconds / launch counts since the last collect into ms[DM4D_K_COUNT] /

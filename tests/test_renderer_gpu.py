@@ -57,7 +57,12 @@ def test_batch_forward_matches_oracle_chain():
     # ---- oracle chain ----
     node = activate_node_deltas(*net_cpu(graph.node_xyz, ts))
     ref = SO.deform_gaussians(scene, graph, *node)
-    Vm, PV, campos, tanx, tany = get_cam_info_gaussian(c2w, fovy, fovy)
+    # the oracle consumes the camera block the GPU actually rasterized (GPU and CPU matrix inverses differ by
+    # ~1e-7, which is beyond the oracle's threshold-ambiguity margin); CPU/GPU camera agreement is checked here
+    Vc, PVc, _, tanxc, tanyc = get_cam_info_gaussian(c2w, fovy, fovy)
+    vpb = ren.last_view_params.cpu()
+    Vm, PV, tanx, tany = vpb[:, 0:16].reshape(-1, 4, 4), vpb[:, 16:32].reshape(-1, 4, 4), vpb[:, 35], vpb[:, 36]
+    assert (Vm - Vc).abs().max() < 1e-5 and (PV - PVc).abs().max() < 1e-5 and (tanx - tanxc).abs().max() < 1e-6
     P = scene.n_gaussians
     orc, oks = [], []
     color6 = torch.zeros(B, 6, H, W); depth = torch.zeros(B, 1, H, W); alpha = torch.zeros(B, 1, H, W)
@@ -119,3 +124,74 @@ def test_batch_forward_matches_oracle_chain():
     assert checked >= 8
     # screen-space mean gradients are exposed like the reference's viewspace_points
     assert out["viewspace_points"].grad is not None and out["viewspace_points"].grad.shape == (B, P, 3)
+
+
+def test_static_stage_step_c1_geometry():
+    """BASELINE config 1 (static refine, no SDS): 10k-face sphere, 30k bound Gaussians, 256x256, 1 view —
+    batch_forward on the static getters and gradients to every learnable SuGaR tensor vs the oracle chain."""
+    torch.manual_seed(0)
+    B, H, W = 1, 256, 256
+    scene = synthetic.make_sugar_scene(10_000, g=3)
+    # anisotropic in-plane scales and non-trivial in-plane rotations: with the isotropic initialisation the
+    # gradient w.r.t. the complex rotation is identically zero (pure rounding noise on both sides)
+    gen = torch.Generator().manual_seed(11)
+    scene.log_scales = scene.log_scales + 0.4 * torch.randn(scene.log_scales.shape, generator=gen)
+    scene.complex_rot = torch.nn.functional.normalize(torch.randn(scene.complex_rot.shape, generator=gen), dim=-1)
+    graph = synthetic.make_deform_graph(scene.verts, 16, 4)
+    geo = DynamicSuGaRGeometry(scene, graph, None, static_learnable=True).to(DEV)
+    ren = DiffGaussianBatchRenderer(geo)
+    c2w, fovy = synthetic.random_orbit_cameras(B, seed=5)
+    rays_o, rays_d = make_rays(c2w, fovy, H, W)
+    batch = {"c2w": c2w.to(DEV), "fovy": fovy.to(DEV), "height": H, "width": W, "rays_o": rays_o.to(DEV), "rays_d": rays_d.to(DEV)}
+    geo.update_step(0, 0)
+    out = ren.batch_forward(batch)
+
+    leaf = lambda t: t.detach().double().clone().requires_grad_(True)
+    verts, cplx, lsc, dens, sh = leaf(scene.verts), leaf(scene.complex_rot), leaf(scene.log_scales), leaf(scene.densities), leaf(scene.sh_dc)
+    means = SO.sugar_points(verts, scene.faces, scene.bary.double())
+    rots = SO.sugar_quaternions(verts, scene.faces, cplx, scene.g)
+    scales = SO.sugar_scaling(lsc, scene.thickness)
+    opac = SO.sugar_opacity(dens)
+    cols = SO.sugar_points_rgb(sh)
+    nrm = SO.faces_normals(verts, scene.faces).repeat_interleave(scene.g, dim=0)
+    vpb = ren.last_view_params.cpu()
+    Vm, PV, tanx, tany = vpb[:, 0:16].reshape(-1, 4, 4), vpb[:, 16:32].reshape(-1, 4, 4), vpb[:, 35], vpb[:, 36]
+    P = scene.n_gaussians
+    o = RasterOracle(P, H, W, 6, "f32")
+    # getters: GPU (fp32) vs oracle (fp64)
+    cpu = lambda t: t.detach().cpu()
+    for got, want in ((geo.get_xyz, means), (geo.get_scaling, scales), (geo.get_opacity, opac), (geo.get_points_rgb(), cols),
+                      (geo.get_gs_normals, nrm)):
+        assert Hh.rel_linf(cpu(got).double().numpy(), want.detach().numpy()) <= 1e-5
+    sgn = torch.sign((cpu(geo.get_rotation).double() * rots.detach()).sum(-1, keepdim=True))
+    assert Hh.rel_linf((cpu(geo.get_rotation).double() * sgn).numpy(), rots.detach().numpy()) <= 1e-5
+    # the oracle rasterizes exactly the fp32 attributes the GPU rasterized (thin 1e-6 Gaussians make the image
+    # sensitive to 1e-7 input differences beyond the threshold-ambiguity margin)
+    feat = torch.cat([cpu(geo.get_points_rgb()), cpu(geo.get_gs_normals)], dim=1)
+    c, r, d, a = o.forward(cpu(geo.get_xyz).numpy(), cpu(geo.get_scaling).numpy(), cpu(geo.get_rotation).numpy(),
+                           cpu(geo.get_opacity).numpy(), feat.numpy(), Vm[0].numpy(), PV[0].numpy(), float(tanx[0]),
+                           float(tany[0]), np.ones(6, np.float32))
+    ok = torch.from_numpy(~o.ambiguous)[None]
+    assert np.array_equal(out["radii"][0].cpu().numpy(), r)
+    got_rgb = out["comp_rgb"].detach().cpu().permute(0, 3, 1, 2)[0]
+    assert ((got_rgb - torch.from_numpy(c[:3]).clamp(0, 1)).abs() * ok).max() <= 1e-4
+    got_a = out["comp_mask"].detach().cpu().permute(0, 3, 1, 2)[0]
+    assert ((got_a - torch.from_numpy(a)).abs() * ok).max() <= 1e-4
+
+    g = torch.Generator().manual_seed(2)
+    color6 = torch.from_numpy(c)
+    inside = ((color6[:3] > 0) & (color6[:3] < 1)).float()
+    gC = torch.randn(3, H, W, generator=g) * ok * inside
+    gA = torch.randn(1, H, W, generator=g) * ok
+    loss = (out["comp_rgb"].permute(0, 3, 1, 2)[0] * gC.to(DEV)).sum() + (out["comp_mask"].permute(0, 3, 1, 2)[0] * gA.to(DEV)).sum()
+    loss.backward()
+    gr = o.backward(torch.cat([gC, torch.zeros(3, H, W)]).numpy(), None, gA.numpy())
+    t = lambda k: torch.from_numpy(gr[k]).double()
+    torch.autograd.backward([means, rots, scales, opac, cols],
+                            [t("means3D"), t("rotations") * sgn, t("scales"), t("opacities"), t("colors")[:, :3]])
+    pairs = {"_points": verts, "_quaternions": cplx, "_scales": lsc, "all_densities": dens, "_sh_coordinates_dc": sh}
+    for name, ref in pairs.items():
+        got = getattr(geo, name).grad
+        assert got is not None, name
+        err = Hh.rel_linf(got.cpu().double().numpy(), ref.grad.numpy())
+        assert err <= 2e-3, f"static grad {name}: rel Linf {err}"

@@ -118,3 +118,27 @@ def test_identity_deformation_is_identity_gpu():
         d(scene.verts), d(scene.faces.int()), d(graph.nbr_idx.int()), d(graph.nbr_w), d(scene.bary), rq)
     assert (verts.cpu() - scene.verts[None]).abs().max() < 1e-6
     assert (qalign(rots, rq[None]) - rq[None]).abs().max() < 1e-6
+
+
+def test_rest_frames_backward_static_stage():
+    """Static stage (BASELINE config 1): vertices and in-plane rotations are learnable; gradients of the
+    rest-pose quaternions / normals vs oracle autograd (fp64)."""
+    scene = synthetic.make_sugar_scene(1_200, g=3)
+    gen = torch.Generator().manual_seed(5)
+    verts = (scene.verts + 0.01 * torch.randn(scene.verts.shape, generator=gen)).double().requires_grad_(True)
+    cplx = torch.randn(scene.complex_rot.shape, generator=gen).double().requires_grad_(True)
+    q_ref = SO.sugar_quaternions(verts, scene.faces, cplx, scene.g)
+    n_ref = SO.faces_normals(verts, scene.faces).repeat_interleave(scene.g, dim=0)
+    gq = torch.randn(q_ref.shape, generator=gen).double()
+    gn = torch.randn(n_ref.shape, generator=gen).double()
+    ((q_ref * gq).sum() + (n_ref * gn).sum()).backward()
+
+    v = verts.detach().float().to(DEV).requires_grad_(True)
+    c = cplx.detach().float().to(DEV).requires_grad_(True)
+    q, n = skinning.sugar_rest_frames(v, scene.faces.int().to(DEV), c, scene.g)
+    sgn = torch.sign((q.detach().cpu().double() * q_ref.detach()).sum(-1, keepdim=True))
+    assert Hh.rel_linf(q.detach().cpu().double() * sgn, q_ref.detach()) <= TOL_FWD
+    assert Hh.rel_linf(n.detach().cpu().double(), n_ref.detach()) <= TOL_FWD
+    ((q * (gq * sgn).float().to(DEV)).sum() + (n * gn.float().to(DEV)).sum()).backward()
+    assert Hh.rel_linf(v.grad.cpu().double(), verts.grad) <= Hh.TOL_GRAD
+    assert Hh.rel_linf(c.grad.cpu().double(), cplx.grad) <= Hh.TOL_GRAD
