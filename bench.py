@@ -460,6 +460,12 @@ def main():
     faulthandler.enable()
     faulthandler.dump_traceback_later(int(os.environ.get("DM4D_BENCH_WATCHDOG_S", "420")), exit=True)   # never hang a GPU box
     args = parse()
+    # stdout must carry exactly ONE JSON line: libraries (e.g. NCCL's version banner) write to fd 1, so route fd 1
+    # to stderr while running and keep the real stdout for the result line.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     try:
         out = run_reference(args) if args.impl == "reference" else run_ours(args)
     except BaseException:
