@@ -126,8 +126,14 @@ __global__ void __launch_bounds__(DM4D_BLOCK) scatter_kernel(RasterLayout L) {
 }
 
 // ---- per-tile sort ------------------------------------------------------------------------------
-constexpr int SORT_CHUNK = 4096;   // keys held in shared memory (32 KB)
-constexpr int SORT_THREADS = 512;
+#ifndef DM4D_SORT_CHUNK
+#define DM4D_SORT_CHUNK 4096
+#endif
+#ifndef DM4D_SORT_THREADS
+#define DM4D_SORT_THREADS 512
+#endif
+constexpr int SORT_CHUNK = DM4D_SORT_CHUNK;     // keys held in shared memory (8 B each)
+constexpr int SORT_THREADS = DM4D_SORT_THREADS;
 constexpr unsigned long long KEY_INF = 0xffffffffffffffffull;
 
 // Single-direction bitonic network on `n` real keys padded virtually with +inf up to `npow2`:
@@ -154,9 +160,10 @@ __device__ void smem_network(unsigned long long* sk, int cn /* pow2 <= SORT_CHUN
         } else {
             int jtop;
             if (k <= cn) {
+                const int hm = (k >> 1) - 1;      // k, j are powers of two: index math with masks, no divisions
                 for (int t = threadIdx.x; t < cn / 2; t += blockDim.x) {
-                    const int blk = t / (k / 2), off = t % (k / 2);
-                    cmpx(sk, blk * k + off, blk * k + (k - 1 - off));
+                    const int off = t & hm, base = (t & ~hm) << 1;
+                    cmpx(sk, base + off, base + (k - 1 - off));
                 }
                 __syncthreads();
                 jtop = k >> 2;
@@ -164,7 +171,10 @@ __device__ void smem_network(unsigned long long* sk, int cn /* pow2 <= SORT_CHUN
                 jtop = cn >> 1;
             }
             for (int j = jtop; j >= 64; j >>= 1) {
-                for (int t = threadIdx.x; t < cn / 2; t += blockDim.x) cmpx(sk, ((t / j) * 2 * j) + (t % j), ((t / j) * 2 * j) + (t % j) + j);
+                for (int t = threadIdx.x; t < cn / 2; t += blockDim.x) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    cmpx(sk, i, i + j);
+                }
                 __syncthreads();
             }
             jwarp = min(jtop, 32);
@@ -173,14 +183,15 @@ __device__ void smem_network(unsigned long long* sk, int cn /* pow2 <= SORT_CHUN
             unsigned long long* base = sk + sp * S;
             if (flip_local) {
                 if (lane < S / 2) {
-                    const int blk = lane / (k / 2), off = lane % (k / 2);
-                    cmpx(base, blk * k + off, blk * k + (k - 1 - off));
+                    const int hm = (k >> 1) - 1;
+                    const int off = lane & hm, b0 = (lane & ~hm) << 1;
+                    cmpx(base, b0 + off, b0 + (k - 1 - off));
                 }
                 __syncwarp();
             }
             for (int j = jwarp; j > 0; j >>= 1) {
                 if (lane < S / 2) {
-                    const int i = ((lane / j) * 2 * j) + (lane % j);
+                    const int i = ((lane & ~(j - 1)) << 1) | (lane & (j - 1));
                     cmpx(base, i, i + j);
                 }
                 __syncwarp();
@@ -229,7 +240,7 @@ __device__ __forceinline__ void pack_record(const float4* __restrict__ src, floa
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) sort_pack_kernel(RasterLayout L) {
-    __shared__ unsigned long long sk[SORT_CHUNK];
+    extern __shared__ __align__(16) unsigned long long sk[];   // [SORT_CHUNK]
     if (L.hdr->overflow) return;
     const int tile = (int)L.tile_order[blockIdx.x];   // global (view, tile) index, heaviest first
     const unsigned int beg = L.tile_offset[tile];
@@ -273,14 +284,15 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pack_kernel(RasterLayout L)
     for (int k = 2 * SORT_CHUNK; k <= npow2; k <<= 1) {
         // flip step (span up to k) in global memory
         for (int t = threadIdx.x; t < npow2 / 2; t += blockDim.x) {
-            const int blk = t / (k / 2), off = t % (k / 2);
-            const int i = blk * k + off, j = blk * k + (k - 1 - off);
+            const int hm = (k >> 1) - 1;
+            const int off = t & hm, base = (t & ~hm) << 1;
+            const int i = base + off, j = base + (k - 1 - off);
             if (j < n) cmpx(gk, i, j);
         }
         __syncthreads();
         for (int j = k >> 2; j >= SORT_CHUNK; j >>= 1) {
             for (int t = threadIdx.x; t < npow2 / 2; t += blockDim.x) {
-                const int i = ((t / j) * 2 * j) + (t % j);
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 if (i + j < n) cmpx(gk, i, i + j);
             }
             __syncthreads();
@@ -331,7 +343,16 @@ int launch_scatter_sort_pack(const RasterLayout& L, cudaStream_t s) {
     if (n == 0) return DM4D_OK;
     { KernelTimer kt(DM4D_K_SCATTER, s); scatter_kernel<<<(unsigned)((n + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(L); }
     DM4D_CUDA_CHECK(cudaGetLastError());
-    { KernelTimer kt(DM4D_K_SORT_PACK, s); sort_pack_kernel<<<(unsigned)(L.n_views * L.tiles), SORT_THREADS, 0, s>>>(L); }
+    {
+        static bool configured = false;
+        const size_t smem = (size_t)SORT_CHUNK * sizeof(unsigned long long);
+        if (!configured) {
+            DM4D_CUDA_CHECK(cudaFuncSetAttribute(sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        KernelTimer kt(DM4D_K_SORT_PACK, s);
+        sort_pack_kernel<<<(unsigned)(L.n_views * L.tiles), SORT_THREADS, smem, s>>>(L);
+    }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }
