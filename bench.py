@@ -318,16 +318,30 @@ def run_ours(args):
                                       reduce_fn=(lambda flat: dist.all_reduce(flat)) if dist is not None else None)
     h2d, d2h = streamed.h2d_bytes, streamed.d2h_bytes
     log("e2e")
-    for _ in range(3):
-        streamed.step()
-    streamed.drain()
     e_steps = max(3, args.steps)
+    if args.no_graph or dist is not None:      # NCCL exchange stays eager (outside graphs)
+        streamed.run_many(3)                   # warm-up
+        torch.cuda.synchronize()
+        run_region = lambda: streamed.run_many(e_steps)
+    else:                                      # the whole K-step pipelined region is ONE graph: immune to host jitter
+        # warm up on a side stream: autograd binds the leaves' AccumulateGrad nodes to the stream of their first
+        # backward, and the legacy default stream may not take part in a capture
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            streamed.run_many(3)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        region = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(region):
+            streamed.run_many(e_steps)
+        region.replay()
+        torch.cuda.synchronize()
+        run_region = region.replay
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(e_steps):
-        streamed.step()
-    streamed.drain()
+    run_region()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)

@@ -201,19 +201,11 @@ __device__ void smem_network(unsigned long long* sk, int cn /* pow2 <= SORT_CHUN
     }
 }
 
-// Minimum of q(x,y) = cx x^2 + 2 cy x y + cz y^2 (positive definite) over the rectangle [x0,x1] x [y0,y1].
-__device__ __forceinline__ float min_quad_rect(float cx, float cy, float cz, float x0, float x1, float y0, float y1) {
-    if (x0 <= 0.f && 0.f <= x1 && y0 <= 0.f && 0.f <= y1) return 0.f;
-    auto q = [&](float x, float y) { return cx * x * x + 2.f * cy * x * y + cz * y * y; };
-    const float icz = 1.f / cz, icx = 1.f / cx;
-    const float ya = fminf(fmaxf(-cy * x0 * icz, y0), y1), yb = fminf(fmaxf(-cy * x1 * icz, y0), y1);
-    const float xa = fminf(fmaxf(-cy * y0 * icx, x0), x1), xb = fminf(fmaxf(-cy * y1 * icx, x0), x1);
-    return fminf(fminf(q(x0, ya), q(x1, yb)), fminf(q(xa, y0), q(xb, y1)));
-}
-
 // Copies one projected record into the sorted stream, replacing the contribution threshold by the tile-local
-// strip mask: bit s set <=> some pixel of rows (2s, 2s+1) x the tile's 16 columns can reach alpha >= 1/255
-// (exact ellipse-vs-strip test, conservative by the margins; never drops a contributing pixel).
+// strip mask: bit s set <=> some pixel of rows (2s, 2s+1) x the tile's 16 columns can reach alpha >= 1/255.
+// Exact ellipse-vs-strip test: the minimum of q(x,y) = cx x^2 + 2 cy x y + cz y^2 (positive definite) over the
+// strip rectangle is 0 if it contains the centre, else it lies on one of the four edges.  Conservative by the
+// margins; never drops a contributing pixel.
 __device__ __forceinline__ void pack_record(const float4* __restrict__ src, float4* __restrict__ dst, int r4,
                                             float tile_x0, float tile_y0) {
     const float4 a = src[0];
@@ -226,10 +218,22 @@ __device__ __forceinline__ void pack_record(const float4* __restrict__ src, floa
             mask = 0xffu;
         } else {
             const float x0 = tile_x0 - a.x - 0.01f, x1 = tile_x0 + 15.f - a.x + 0.01f;
+            const float icx = 1.f / cx, icz = 1.f / cz;
+            const float yx0 = -cy * x0 * icz, yx1 = -cy * x1 * icz;       // unconstrained minimisers on the edges x = x0, x1
+            const float qx0 = cx * x0 * x0, qx1 = cx * x1 * x1;
+            const bool x_in = x0 <= 0.f && 0.f <= x1;
+            auto qe = [&](float qxx, float x, float y) { return qxx + (2.f * cy * x + cz * y) * y; };
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
-                const float y0 = tile_y0 + (float)(2 * s) - a.y - 0.01f;
-                if (min_quad_rect(cx, cy, cz, x0, x1, y0, y0 + 1.02f) <= thr) mask |= 1u << s;
+                const float y0 = tile_y0 + (float)(2 * s) - a.y - 0.01f, y1 = y0 + 1.02f;
+                float qmin = 0.f;
+                if (!(x_in && y0 <= 0.f && 0.f <= y1)) {
+                    const float ya = fminf(fmaxf(yx0, y0), y1), yb = fminf(fmaxf(yx1, y0), y1);
+                    const float xa = fminf(fmaxf(-cy * y0 * icx, x0), x1), xb = fminf(fmaxf(-cy * y1 * icx, x0), x1);
+                    qmin = fminf(fminf(qe(qx0, x0, ya), qe(qx1, x1, yb)),
+                                 fminf(qe(cx * xa * xa, xa, y0), qe(cx * xb * xb, xb, y1)));
+                }
+                if (qmin <= thr) mask |= 1u << s;
             }
         }
     }

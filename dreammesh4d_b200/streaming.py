@@ -45,6 +45,7 @@ class HostStreamedRasterStep:
         self.compute_done = [None, None]          # event: compute finished reading buffer k
         self.d2h_done: Optional[torch.cuda.Event] = None
         self.inflight: deque = deque()
+        self.retain_all = False                   # set while capturing into a CUDA graph (see run_many)
         self.last_state: Optional[R.RasterState] = None
 
     def step(self) -> None:
@@ -90,14 +91,30 @@ class HostStreamedRasterStep:
         with torch.no_grad(), torch.cuda.stream(self.d2h):
             self.d2h.wait_event(ev_c)
             for n, t in outs.items():
-                t.record_stream(self.d2h)
+                if not self.retain_all:
+                    t.record_stream(self.d2h)
                 self.out[n].copy_(t, non_blocking=True)
             self.d2h_done = torch.cuda.Event()
             self.d2h_done.record(self.d2h)
         self.inflight.append(outs)
-        while len(self.inflight) > 2:
+        while not self.retain_all and len(self.inflight) > 2:
             self.inflight.popleft()
         self.i += 1
+
+    def run_many(self, k: int) -> None:
+        """``k`` pipelined steps followed by ``drain()``.  Safe to capture into ONE CUDA graph (the copy streams are
+        forked from and joined back into the current stream; every output stays referenced until the capture ends,
+        so the graph's memory pool never recycles a block that another stream still reads)."""
+        capturing = torch.cuda.is_current_stream_capturing()
+        self.retain_all = capturing
+        self.compute_done = [None, None]
+        for _ in range(k):
+            self.step()
+        self.drain()
+        self.retain_all = False
+        if not capturing:
+            while len(self.inflight) > 2:
+                self.inflight.popleft()
 
     def drain(self) -> None:
         """Makes the current stream wait for every outstanding copy (end of a timed region / before reading ``out``)."""
