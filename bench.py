@@ -64,6 +64,65 @@ def build_cameras(rank: int):
     return get_cam_info_gaussian(c2w, fovy, fovy)
 
 
+def cams_c2w_fovy(rank: int):
+    from dreammesh4d_b200 import synthetic
+    return synthetic.random_orbit_cameras(VIEWS, seed=2 + rank), synthetic.random_orbit_cameras(VIEWS, seed=102 + rank)
+
+
+def train_step_ms(scene, graph, cams, dev, dist, steps: int):
+    """One dynamic-stage optimizer step on the hot path WITHOUT the Zero123 guidance (weights are not available
+    offline): HexPlane/MLP deformation (PyTorch) -> fused skinning -> 6-channel batched rasterizer -> post-ops ->
+    image losses (MSE rgb + mask vs fixed targets, the reference-view terms of sugar_4dgen.py:161-170) -> backward
+    -> control-node gradient exchange -> Adam.  Two substeps of 8 views each, as sugar_4dgen.py:411-417."""
+    from dreammesh4d_b200.deformation import HexPlaneDeformation
+    from dreammesh4d_b200.geometry import DynamicSuGaRGeometry
+    from dreammesh4d_b200.renderer import DiffGaussianBatchRenderer
+    from dreammesh4d_b200.trainstep import DynamicStageStep
+    torch.manual_seed(0)
+    net = HexPlaneDeformation().to(dev)
+    with torch.no_grad():
+        for head, sdev in ((net.deformation_net.pos_deform, 0.01), (net.deformation_net.rotations_deform, 0.05),
+                           (net.deformation_net.scales_deform, 0.01), (net.deformation_net.opacity_deform, 0.3)):
+            head.feature_out[1].weight.normal_(0, sdev)
+    geo = DynamicSuGaRGeometry(scene, graph, net).to(dev)
+    ren = DiffGaussianBatchRenderer(geo)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99), eps=1e-15)
+    batches = []
+    for (c2w, fovy) in cams:
+        focal = 0.5 * H / torch.tan(0.5 * fovy)
+        j, i = torch.meshgrid(torch.arange(H, dtype=torch.float32) + 0.5, torch.arange(W, dtype=torch.float32) + 0.5, indexing="ij")
+        dirs = torch.stack([(i[None] - W / 2) / focal[:, None, None], -(j[None] - H / 2) / focal[:, None, None],
+                            -torch.ones(len(fovy), H, W)], dim=-1)
+        rays_d = (dirs[..., None, :] * c2w[:, None, None, :3, :3]).sum(-1)
+        rays_o = c2w[:, None, None, :3, 3].expand_as(rays_d)
+        batches.append({"c2w": c2w.to(dev), "fovy": fovy.to(dev), "height": H, "width": W,
+                        "timestamp": torch.linspace(0, 1, VIEWS + 2)[1:-1].to(dev), "rays_o": rays_o.contiguous().to(dev),
+                        "rays_d": rays_d.contiguous().to(dev),
+                        "rgb": torch.rand(VIEWS, H, W, 3, device=dev), "mask": (torch.rand(VIEWS, H, W, 1, device=dev) > 0.5).float()})
+
+    def loss_fn(out, batch):
+        return 5000.0 * torch.nn.functional.mse_loss(out["comp_rgb"], batch["rgb"]) + \
+            500.0 * torch.nn.functional.mse_loss(out["comp_mask"], batch["mask"])
+
+    stepper = DynamicStageStep(geo, ren, opt, loss_fn)
+    stepper(batches, 0)                                   # sizes the binning workspace with one read-back
+    ren.capacity = int(ren.last_state.status()[0] * 1.3) + 4096
+    for i in range(3):
+        stepper(batches, i)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        ev[i][0].record()
+        stepper(batches, i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in ev)
+    return {"ms_median": ms[len(ms) // 2], "ms_mean": sum(ms) / len(ms), "steps": steps,
+            "what": "optimizer step of the dynamic stage on the hot path: 2 substeps x 8 views x 512^2, HexPlane+MLP (PyTorch) -> "
+                    "fused skinning -> 6-channel rasterizer -> post-ops -> MSE rgb+mask -> backward -> node-gradient exchange -> Adam; "
+                    "Zero123 SDS excluded (weights unavailable offline); eager launches, CUDA events"}
+
+
 def gaussian_sets_gpu(scene, graph, node, dev):
     """Per-timestamp Gaussian sets produced by the product path (fused skinning kernels), on the GPU."""
     from dreammesh4d_b200 import skinning, synthetic
@@ -350,6 +409,14 @@ def run_ours(args):
         raise SystemExit("bin capacity overflow in the e2e region — result invalid")
     clocks = sampler.result()
 
+    # ---- context: full hot-path optimizer step (first half of BASELINE's metric, "train-step ms") ----
+    train = None
+    try:
+        train = train_step_ms(scene, graph, cams_c2w_fovy(rank), dev, dist, steps=max(5, min(args.steps, 20)))
+        log(f"train step: {train['ms_median']:.3f} ms")
+    except Exception as e:      # context only: never fail the bench line on it
+        log(f"train-step measurement skipped: {type(e).__name__}: {e}")
+
     # ---- max over ranks ----
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -400,7 +467,7 @@ def run_ours(args):
                     "how": "HostStreamedRasterStep: pinned host sets + image gradients -> H2D | fwd+bwd (+exchange) | D2H of images and all gradients to pinned host, software-pipelined across consecutive steps on 3 streams; whole region timed with CUDA events (235 MB/step > L2, no flush)",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps},
             "gpu_launches": launches_per_step * args.steps,
-            "kernels": kern, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "kernels": kern, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "train_step": train,
         }
     if out is not None:
         print(json.dumps(out), flush=True)

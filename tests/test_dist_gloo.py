@@ -42,3 +42,45 @@ def test_gradient_exchange_world2_gloo():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def _worker_nodegrad(rank, world, port, ret):
+    """node_attribute_backward: gathered replay == sum over ranks of the per-rank parameter gradients."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dreammesh4d_b200.deformation import HexPlaneDeformation
+        from dreammesh4d_b200.geometry import activate_node_deltas
+        from dreammesh4d_b200.trainstep import node_attribute_backward
+        torch.manual_seed(0)
+        net = HexPlaneDeformation(base_res=(8, 8, 8, 5), multires=(1, 2))
+        with torch.no_grad():
+            for head in (net.deformation_net.pos_deform, net.deformation_net.rotations_deform,
+                         net.deformation_net.scales_deform, net.deformation_net.opacity_deform):
+                head.feature_out[1].weight.normal_(0, 0.1)
+        xyz = torch.rand(7, 3) - 0.5
+        ts_all = torch.linspace(0.1, 0.9, 2 * world)
+        g = torch.Generator().manual_seed(1)
+        shapes = [(2 * world, 7, 3), (2 * world, 7, 4), (2 * world, 7, 3, 3), (2 * world, 7, 1)]
+        g_all = [torch.randn(s, generator=g) for s in shapes]
+        # reference: single-process backward over the global batch
+        attrs = activate_node_deltas(*net(xyz, ts_all))
+        torch.autograd.backward(list(attrs), g_all)
+        want = [p.grad.clone() for p in net.parameters() if p.grad is not None]
+        net.zero_grad(set_to_none=True)
+        # distributed: every rank holds its slice of timestamps / node gradients
+        sl = slice(2 * rank, 2 * rank + 2)
+        node_attribute_backward(net, xyz, ts_all[sl], [t[sl] for t in g_all])
+        got = [p.grad for p in net.parameters() if p.grad is not None]
+        ret[rank] = len(got) == len(want) and all(torch.allclose(a, b, rtol=1e-5, atol=1e-7) for a, b in zip(got, want))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_node_attribute_gradient_exchange_world2_gloo():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_nodegrad, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]

@@ -195,3 +195,40 @@ def test_static_stage_step_c1_geometry():
         assert got is not None, name
         err = Hh.rel_linf(got.cpu().double().numpy(), ref.grad.numpy())
         assert err <= 2e-3, f"static grad {name}: rel Linf {err}"
+
+
+def test_dynamic_stage_step_matches_end_to_end_autograd():
+    """DynamicStageStep (detach at the control-node attributes, exchange, replayed network backward) produces the same
+    parameter gradients as plain end-to-end autograd through the deformation network, and an Adam step runs."""
+    from dreammesh4d_b200.trainstep import DynamicStageStep
+    torch.manual_seed(0)
+    B, H, W = 2, 64, 64
+    scene = synthetic.make_sugar_scene(600, g=3)
+    graph = synthetic.make_deform_graph(scene.verts, 16, 4)
+    net = HexPlaneDeformation(base_res=(16, 16, 16, 5), multires=(1, 2))
+    with torch.no_grad():
+        for head, s in ((net.deformation_net.pos_deform, 0.02), (net.deformation_net.rotations_deform, 0.1),
+                        (net.deformation_net.scales_deform, 0.03), (net.deformation_net.opacity_deform, 0.5)):
+            head.feature_out[1].weight.normal_(0, s)
+    geo = DynamicSuGaRGeometry(scene, graph, net).to(DEV)
+    ren = DiffGaussianBatchRenderer(geo)
+    c2w, fovy = synthetic.random_orbit_cameras(B, seed=3)
+    rays_o, rays_d = make_rays(c2w, fovy, H, W)
+    batch = {"c2w": c2w.to(DEV), "fovy": fovy.to(DEV), "height": H, "width": W,
+             "timestamp": torch.tensor([0.3, 0.7], device=DEV), "rays_o": rays_o.to(DEV), "rays_d": rays_d.to(DEV),
+             "rgb": torch.rand(B, H, W, 3, device=DEV), "mask": torch.ones(B, H, W, 1, device=DEV)}
+    loss_fn = lambda out, b: torch.nn.functional.mse_loss(out["comp_rgb"], b["rgb"]) + torch.nn.functional.mse_loss(out["comp_mask"], b["mask"])
+    # end-to-end autograd
+    geo.update_step(0, 0)
+    loss_fn(ren.batch_forward(batch), batch).backward()
+    want = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    # the step (SGD with lr 0 keeps the parameters, so the gradients stay comparable)
+    opt = torch.optim.SGD(net.parameters(), lr=0.0)
+    loss = DynamicStageStep(geo, ren, opt, loss_fn)([batch], 0)
+    assert torch.isfinite(loss)
+    checked = 0
+    for n, p in net.named_parameters():
+        if n in want and float(want[n].abs().max()) > 0:
+            assert Hh.rel_linf(p.grad.cpu().numpy(), want[n].cpu().numpy()) <= 1e-4, n
+            checked += 1
+    assert checked >= 8
