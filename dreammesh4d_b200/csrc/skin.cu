@@ -609,3 +609,75 @@ extern "C" int dm4d_sugar_rest_frames_backward(const float* verts, const int32_t
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// ARAP energy on the deformed vertices
+// ------------------------------------------------------------------------------------------------
+// E_t = sum_i sum_{j in N(i)} w_ij || (x'_i - x'_j) - R(q_i) (x_i - x_j) ||^2   with the per-vertex rotations
+// SUPPLIED by the deformation (ARAPCoach.compute_arap_energy with vert_rotations,
+// custom/threestudio-dreammesh4d/utils/arap_utils.py:183-224; called per timestamp from
+// system/sugar_4dgen.py:372-385).  One thread per (timestamp, vertex) walks its one-ring (CSR), and the same
+// pass writes dE/dx' and dE/dq (xyzw, Euclidean), which feed dm4d_skin_backward's dL_dverts_in / dL_dvert_rot_in.
+namespace {
+__global__ void __launch_bounds__(DM4D_BLOCK) arap_energy_kernel(const float* rest_verts, const int32_t* row_ptr,
+                                                                 const int32_t* col, const float* w, int n_t, int V,
+                                                                 const float* verts, const float* vert_rot,
+                                                                 float* energy, float* dverts, float* dvert_rot) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float e_local = 0.f;
+    if (idx < (long long)n_t * V) {
+        const int t = (int)(idx / V), i = (int)(idx - (long long)t * V);
+        const size_t vb = (size_t)t * V;
+        const f3 xi = ld3(rest_verts + (size_t)i * 3), xpi = ld3(verts + (vb + i) * 3);
+        const float4 q = ldq(vert_rot + (vb + i) * 4);
+        f3 gxi = mk3(0, 0, 0);
+        float4 gq = make_float4(0, 0, 0, 0);
+        for (int k = row_ptr[i]; k < row_ptr[i + 1]; ++k) {
+            const int j = col[k];
+            const float wij = w[k];
+            const f3 e = xi - ld3(rest_verts + (size_t)j * 3);
+            const f3 s = (xpi - ld3(verts + (vb + j) * 3)) - qact(q, e);
+            e_local += wij * dot(s, s);
+            const f3 g = (2.f * wij) * s;
+            gxi = gxi + g;
+            if (dverts) {
+                float* pj = dverts + (vb + j) * 3;
+                atomicAdd(pj + 0, -g.x); atomicAdd(pj + 1, -g.y); atomicAdd(pj + 2, -g.z);
+            }
+            float4 dq;
+            qact_bwd(q, e, mk3(0, 0, 0) - g, dq);
+            gq = gq + dq;
+        }
+        if (dverts) {
+            float* pi = dverts + (vb + i) * 3;
+            atomicAdd(pi + 0, gxi.x); atomicAdd(pi + 1, gxi.y); atomicAdd(pi + 2, gxi.z);
+        }
+        if (dvert_rot) *reinterpret_cast<float4*>(dvert_rot + (vb + i) * 4) = gq;
+        // per-timestamp energy: warp-level pre-reduction when the whole warp is in range and in one timestamp
+        const long long w_first = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31), w_last = w_first + 31;
+        if (w_last < (long long)n_t * V && w_first / V == w_last / V) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e_local += __shfl_xor_sync(0xffffffffu, e_local, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(energy + t, e_local);
+        } else {
+            atomicAdd(energy + t, e_local);
+        }
+    }
+}
+}  // namespace
+
+extern "C" int dm4d_arap_energy(const float* rest_verts, const int32_t* row_ptr, const int32_t* col, const float* weights,
+                                int32_t n_t, int32_t V, const float* verts, const float* vert_rot, float* energy,
+                                float* dE_dverts, float* dE_dvert_rot, void* stream) {
+    if (!rest_verts || !row_ptr || !col || !weights || !verts || !vert_rot || !energy || n_t <= 0 || V <= 0) {
+        dm4d_set_error("dm4d_arap_energy: bad argument");
+        return DM4D_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nv = (size_t)n_t * V;
+    DM4D_CUDA_CHECK(cudaMemsetAsync(energy, 0, (size_t)n_t * sizeof(float), s));
+    if (dE_dverts) DM4D_CUDA_CHECK(cudaMemsetAsync(dE_dverts, 0, nv * 3 * sizeof(float), s));
+    { KernelTimer kt(DM4D_K_ARAP, s); arap_energy_kernel<<<(unsigned)((nv + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(rest_verts, row_ptr, col, weights, n_t, V, verts, vert_rot, energy, dE_dverts, dE_dvert_rot); }
+    DM4D_CUDA_CHECK(cudaGetLastError());
+    return DM4D_OK;
+}

@@ -181,6 +181,18 @@ int dm4d_sugar_rest_frames_backward(const float* verts, const int32_t* faces, co
                                     int32_t F, int32_t g, const float* dL_dquaternions, const float* dL_dnormals,
                                     float* dL_dverts, float* dL_dcomplex_rot, void* stream);
 
+/* ARAP energy of the deformed mesh with the rotations supplied by the deformation, per timestamp:
+ *   E_t = sum_i sum_{j in N(i)} w_ij || (x'_i - x'_j) - R(q_i) (x_i - x_j) ||^2
+ * Replaces ARAPCoach.compute_arap_energy(xyz_prime, vert_rotations)
+ * (custom/threestudio-dreammesh4d/utils/arap_utils.py:183-224; caller system/sugar_4dgen.py:372-385).
+ * One-ring as CSR: row_ptr [V+1], col [E] (int32), weights [E] (the cotangent weights of arap_utils.py:100-175).
+ * verts [n_t,V,3] / vert_rot [n_t,V,4] xyzw are dm4d_skin_forward's outputs.  Outputs (overwritten): energy [n_t],
+ * and, if non-NULL, the gradients dE/dverts [n_t,V,3] and dE/dvert_rot [n_t,V,4], which are exactly
+ * dm4d_skin_backward's dL_dverts_in / dL_dvert_rot_in (after scaling by the loss weight). */
+int dm4d_arap_energy(const float* rest_verts, const int32_t* row_ptr, const int32_t* col, const float* weights,
+                     int32_t n_t, int32_t V, const float* verts, const float* vert_rot, float* energy,
+                     float* dE_dverts, float* dE_dvert_rot, void* stream);
+
 /* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel launch).
  * Kernel ids: see DM4D_K_* below.  dm4d_profile_collect synchronises the recorded events, ADDS the
  * elapsed milliseconds / launch counts since the last collect into ms[DM4D_K_COUNT] /
@@ -188,7 +200,7 @@ int dm4d_sugar_rest_frames_backward(const float* verts, const int32_t* faces, co
 enum {
     DM4D_K_PREPROCESS = 0, DM4D_K_SCAN, DM4D_K_SCATTER, DM4D_K_SORT_PACK, DM4D_K_RENDER_FWD,
     DM4D_K_RENDER_BWD, DM4D_K_PREPROCESS_BWD, DM4D_K_SKIN_VERT_FWD, DM4D_K_SKIN_GAUSS_FWD,
-    DM4D_K_SKIN_GAUSS_BWD, DM4D_K_SKIN_VERT_BWD, DM4D_K_REST_FRAMES, DM4D_K_COUNT
+    DM4D_K_SKIN_GAUSS_BWD, DM4D_K_SKIN_VERT_BWD, DM4D_K_REST_FRAMES, DM4D_K_ARAP, DM4D_K_COUNT
 };
 int dm4d_profile_enable(int on);
 int dm4d_profile_collect(double* ms_host, int64_t* launches_host);
