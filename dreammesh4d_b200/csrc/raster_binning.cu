@@ -201,6 +201,69 @@ __device__ void smem_network(unsigned long long* sk, int cn /* pow2 <= SORT_CHUN
     }
 }
 
+// Block-level merge sort of `n` keys held in shared memory (n <= SORT_CHUNK): every thread first sorts MS_E
+// consecutive keys in registers, then log2(n / MS_E) merge passes in which each thread produces MS_E consecutive
+// outputs of its pair of runs (merge-path binary search for the split, then a sequential merge).  About 4x
+// fewer instructions per key than the bitonic network; keys are unique, so the result is the unique sorted order.
+constexpr int MS_E = 8;
+
+__device__ __forceinline__ void cmpswap(unsigned long long& a, unsigned long long& b) {
+    const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo; b = hi;
+}
+
+__device__ void smem_merge_sort(unsigned long long* sk, int n) {
+    const int npad = (n + MS_E - 1) / MS_E * MS_E;
+    const int base = threadIdx.x * MS_E;
+    const bool active = base < npad;
+    unsigned long long r[MS_E];
+    if (active) {
+#pragma unroll
+        for (int e = 0; e < MS_E; ++e) r[e] = sk[base + e];
+        // odd-even merge sorting network for 8 keys (19 comparators)
+        cmpswap(r[0], r[1]); cmpswap(r[2], r[3]); cmpswap(r[4], r[5]); cmpswap(r[6], r[7]);
+        cmpswap(r[0], r[2]); cmpswap(r[1], r[3]); cmpswap(r[4], r[6]); cmpswap(r[5], r[7]);
+        cmpswap(r[1], r[2]); cmpswap(r[5], r[6]);
+        cmpswap(r[0], r[4]); cmpswap(r[1], r[5]); cmpswap(r[2], r[6]); cmpswap(r[3], r[7]);
+        cmpswap(r[2], r[4]); cmpswap(r[3], r[5]);
+        cmpswap(r[1], r[2]); cmpswap(r[3], r[4]); cmpswap(r[5], r[6]);
+#pragma unroll
+        for (int e = 0; e < MS_E; ++e) sk[base + e] = r[e];
+    }
+    __syncthreads();
+    for (int w = MS_E; w < npad; w <<= 1) {
+        if (active) {
+            const int a0 = base & ~(2 * w - 1);            // start of this thread's pair of runs
+            const int b0 = a0 + w;
+            const int lenA = min(w, npad - a0);
+            const int lenB = max(0, min(w, npad - b0));
+            const unsigned long long* A = sk + a0;
+            const unsigned long long* B = sk + b0;
+            const int diag = base - a0;                      // outputs [diag, diag + MS_E) of the merged pair
+            int lo = max(0, diag - lenB), hi = min(diag, lenA);
+            while (lo < hi) {                                // merge path: number of A elements among the first `diag`
+                const int mid = (lo + hi) >> 1;
+                if (A[mid] <= B[diag - 1 - mid]) lo = mid + 1; else hi = mid;
+            }
+            int i = lo, j = diag - lo;
+            unsigned long long av = i < lenA ? A[i] : KEY_INF, bv = j < lenB ? B[j] : KEY_INF;
+#pragma unroll
+            for (int e = 0; e < MS_E; ++e) {
+                const bool takeA = (j >= lenB) || (i < lenA && av <= bv);
+                r[e] = takeA ? av : bv;
+                if (takeA) { ++i; av = i < lenA ? A[i] : KEY_INF; }
+                else { ++j; bv = j < lenB ? B[j] : KEY_INF; }
+            }
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < MS_E; ++e) sk[base + e] = r[e];
+        }
+        __syncthreads();
+    }
+}
+
 // Copies one projected record into the sorted stream, replacing the contribution threshold by the tile-local
 // strip mask: bit s set <=> some pixel of rows (2s, 2s+1) x the tile's 16 columns can reach alpha >= 1/255.
 // Exact ellipse-vs-strip test: the minimum of q(x,y) = cx x^2 + 2 cy x y + cz y^2 (positive definite) over the
@@ -262,9 +325,11 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pack_kernel(RasterLayout L)
     const float tile_x0 = (float)(((tile - v * L.tiles) % L.gx) * DM4D_TILE);
 
     if (npow2 <= SORT_CHUNK) {
-        for (int i = threadIdx.x; i < npow2; i += blockDim.x) sk[i] = i < n ? gk[i] : KEY_INF;
+        const int nfill = max(npow2, (n + MS_E - 1) / MS_E * MS_E);      // the merge sort pads to a multiple of MS_E
+        for (int i = threadIdx.x; i < nfill; i += blockDim.x) sk[i] = i < n ? gk[i] : KEY_INF;
         __syncthreads();
-        smem_network(sk, npow2, 2, npow2);
+        if (MS_E * SORT_THREADS >= SORT_CHUNK) smem_merge_sort(sk, n);
+        else smem_network(sk, npow2, 2, npow2);
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const unsigned int id = (unsigned int)(sk[i] & 0xffffffffull);
             pack_record(grec + (size_t)id * r4, srec + (size_t)i * r4, r4, tile_x0, tile_y0);
