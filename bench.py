@@ -72,7 +72,7 @@ def cams_c2w_fovy(rank: int):
 def train_step_ms(scene, graph, cams, dev, dist, steps: int):
     """One dynamic-stage optimizer step on the hot path WITHOUT the Zero123 guidance (weights are not available
     offline): HexPlane/MLP deformation (PyTorch) -> fused skinning -> 6-channel batched rasterizer -> post-ops ->
-    image losses (MSE rgb + mask vs fixed targets, the reference-view terms of sugar_4dgen.py:161-170) -> backward
+    image losses (MSE rgb + mask vs fixed targets, sugar_4dgen.py:161-170) + ARAP + mesh normal consistency (fused kernels) -> backward
     -> control-node gradient exchange -> Adam.  Two substeps of 8 views each, as sugar_4dgen.py:411-417."""
     from dreammesh4d_b200.deformation import HexPlaneDeformation
     from dreammesh4d_b200.geometry import DynamicSuGaRGeometry
@@ -100,9 +100,15 @@ def train_step_ms(scene, graph, cams, dev, dist, steps: int):
                         "rays_d": rays_d.contiguous().to(dev),
                         "rgb": torch.rand(VIEWS, H, W, 3, device=dev), "mask": (torch.rand(VIEWS, H, W, 1, device=dev) > 0.5).float()})
 
-    def loss_fn(out, batch):
+    from dreammesh4d_b200.arap import ARAPEnergy, face_pairs, mesh_normal_consistency
+    arap = ARAPEnergy(geo._points.detach(), geo._surface_mesh_faces)
+    pairs = face_pairs(geo._surface_mesh_faces)
+
+    def loss_fn(out, batch):       # the loss terms that are live in sugar_dynamic_dg.yaml:135-158 minus the SDS term
+        timed = geo._timed
         return 5000.0 * torch.nn.functional.mse_loss(out["comp_rgb"], batch["rgb"]) + \
-            500.0 * torch.nn.functional.mse_loss(out["comp_mask"], batch["mask"])
+            500.0 * torch.nn.functional.mse_loss(out["comp_mask"], batch["mask"]) + \
+            10.0 * arap(timed["verts"], timed["vert_rot"]).sum() + 100.0 * mesh_normal_consistency(timed["verts"], pairs)
 
     stepper = DynamicStageStep(geo, ren, opt, loss_fn)
     stepper(batches, 0)                                   # sizes the binning workspace with one read-back
@@ -119,7 +125,7 @@ def train_step_ms(scene, graph, cams, dev, dist, steps: int):
     ms = sorted(a.elapsed_time(b) for a, b in ev)
     return {"ms_median": ms[len(ms) // 2], "ms_mean": sum(ms) / len(ms), "steps": steps,
             "what": "optimizer step of the dynamic stage on the hot path: 2 substeps x 8 views x 512^2, HexPlane+MLP (PyTorch) -> "
-                    "fused skinning -> 6-channel rasterizer -> post-ops -> MSE rgb+mask -> backward -> node-gradient exchange -> Adam; "
+                    "fused skinning -> 6-channel rasterizer -> post-ops -> MSE rgb+mask + ARAP + normal consistency -> backward -> node-gradient exchange -> Adam; "
                     "Zero123 SDS excluded (weights unavailable offline); eager launches, CUDA events"}
 
 

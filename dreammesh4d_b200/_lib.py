@@ -62,6 +62,7 @@ SIGNATURES = {
     "dm4d_sugar_rest_frames": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dm4d_sugar_rest_frames_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dm4d_arap_energy": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dm4d_mesh_normal_consistency": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dm4d_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "dm4d_profile_collect": (ctypes.c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
     "dm4d_kernel_name": (c_char_p, [ctypes.c_int]),
@@ -69,7 +70,7 @@ SIGNATURES = {
     "dm4d_version": (ctypes.c_int, []),
 }
 
-K_COUNT = 13
+K_COUNT = 14
 
 _lib = None
 

@@ -71,3 +71,57 @@ class ARAPEnergy:
 
     def __call__(self, verts: torch.Tensor, vert_rot: torch.Tensor) -> torch.Tensor:
         return _ArapFunction.apply(verts, vert_rot, self.rest, self.row_ptr, self.col, self.w)
+
+
+# ---- mesh normal consistency (pytorch3d.loss.mesh_normal_consistency; sugar_4dgen.py:214-225) -------------------
+def face_pairs(faces: torch.Tensor) -> torch.Tensor:
+    """[n_pairs,4] int32 rows (v0, v1, a, b): every pair of faces sharing the undirected edge {v0,v1}, with the
+    vertices a / b opposite to that edge in the two faces (setup, once; manifold edges give exactly one pair)."""
+    f = faces.long().cpu()
+    e = torch.cat([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])              # directed edges, per face corner
+    opp = torch.cat([f[:, 2], f[:, 0], f[:, 1]])
+    lo, hi = e.min(dim=1).values, e.max(dim=1).values
+    key = lo * (int(f.max()) + 1) + hi
+    order = torch.argsort(key, stable=True)
+    key, lo, hi, opp = key[order], lo[order], hi[order], opp[order]
+    # runs of equal keys; manifold edges (runs of exactly two) are handled vectorised, the rest in a small loop
+    change = torch.ones_like(key, dtype=torch.bool)
+    change[1:] = key[1:] != key[:-1]
+    run_start = torch.nonzero(change).flatten()
+    run_len = torch.diff(torch.cat([run_start, torch.tensor([key.numel()])]))
+    two = run_start[run_len == 2]
+    out = [torch.stack([lo[two], hi[two], opp[two], opp[two + 1]], dim=1)]
+    rows = []
+    for st, ln in zip(run_start[run_len > 2].tolist(), run_len[run_len > 2].tolist()):
+        for x in range(st, st + ln):
+            for y in range(x + 1, st + ln):
+                rows.append((int(lo[st]), int(hi[st]), int(opp[x]), int(opp[y])))
+    if rows:
+        out.append(torch.tensor(rows, dtype=torch.long))
+    return torch.cat(out).to(dtype=torch.int32, device=faces.device).reshape(-1, 4)
+
+
+class _NormalConsistencyFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, pairs):
+        l = _lib.lib()
+        if verts.device.type != "cuda":
+            raise _lib.Dm4dError("dreammesh4d_b200 needs CUDA tensors (there is no CPU path)")
+        v = verts.detach().float().contiguous()
+        T, V = v.shape[0], v.shape[1]
+        loss = torch.empty(T, dtype=torch.float32, device=v.device)
+        dv = torch.empty_like(v)
+        check(l.dm4d_mesh_normal_consistency(ptr(pairs), pairs.shape[0], T, V, ptr(v), ptr(loss), ptr(dv),
+                                             torch.cuda.current_stream().cuda_stream), "dm4d_mesh_normal_consistency")
+        ctx.save_for_backward(dv)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dv,) = ctx.saved_tensors
+        return dv * g[:, None, None], None
+
+
+def mesh_normal_consistency(verts: torch.Tensor, pairs: torch.Tensor) -> torch.Tensor:
+    """Scalar loss: mean over the T deformed meshes of the mean over face pairs of 1 - cos(n0, n1)."""
+    return _NormalConsistencyFunction.apply(verts, pairs).mean()

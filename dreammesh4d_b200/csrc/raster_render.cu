@@ -383,9 +383,10 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
                     const float dG_ddely = -gdy * b.x - gdx * a.w;
                     gv[0] = dL_dG * dG_ddelx * ddelx_dx;
                     gv[1] = dL_dG * dG_ddely * ddely_dy;
-                    gv[2] = -0.5f * gdx * dx * dL_dG;
-                    gv[3] = -0.5f * gdx * dy * dL_dG;
-                    gv[4] = -0.5f * gdy * dy * dL_dG;
+                    const float hx = -0.5f * dL_dG * gdx, hy = -0.5f * dL_dG * gdy;   // shared factors of the conic terms
+                    gv[2] = hx * dx;
+                    gv[3] = hx * dy;
+                    gv[4] = hy * dy;
                     gv[5] = G * dL_dalpha;
                 }
                 const float tot = warp_reduce_scatter16(gv, lane);

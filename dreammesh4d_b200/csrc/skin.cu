@@ -681,3 +681,62 @@ extern "C" int dm4d_arap_energy(const float* rest_verts, const int32_t* row_ptr,
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// mesh normal consistency on the deformed meshes
+// ------------------------------------------------------------------------------------------------
+// pytorch3d.loss.mesh_normal_consistency as called at custom/threestudio-dreammesh4d/system/sugar_4dgen.py:214-225
+// (lambda_normal_consistency = 100): for every pair of faces sharing an edge (v0,v1) with opposite vertices a, b:
+//   n0 = (v1-v0) x (a-v0),  n1 = (v1-v0) x (b-v0),  term = 1 - cos(n0, -n1);   loss = mean over pairs, mean over meshes.
+// One thread per (timestamp, pair); the same pass writes d loss_t / d verts (scaled by 1/pairs).
+namespace {
+__global__ void __launch_bounds__(DM4D_BLOCK) normal_consistency_kernel(const int32_t* pairs, int n_pairs, int n_t, int V,
+                                                                        const float* verts, float* loss, float* dverts) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_t * n_pairs) return;
+    const int t = (int)(idx / n_pairs), p = (int)(idx - (long long)t * n_pairs);
+    const int i0 = pairs[p * 4], i1 = pairs[p * 4 + 1], ia = pairs[p * 4 + 2], ib = pairs[p * 4 + 3];
+    const size_t vb = (size_t)t * V;
+    const f3 v0 = ld3(verts + (vb + i0) * 3), v1 = ld3(verts + (vb + i1) * 3), a = ld3(verts + (vb + ia) * 3),
+             b = ld3(verts + (vb + ib) * 3);
+    const f3 e = v1 - v0, ea = a - v0, eb = b - v0;
+    const f3 n0 = cross(e, ea);
+    const f3 m1 = mk3(0, 0, 0) - cross(e, eb);                 // -n1
+    // torch.cosine_similarity: x.y / (max(|x|, eps) * max(|y|, eps)), eps = 1e-8
+    const float l0 = sqrtf(dot(n0, n0)), l1 = sqrtf(dot(m1, m1));
+    const float c0 = fmaxf(l0, 1e-8f), c1 = fmaxf(l1, 1e-8f);
+    const float cosv = dot(n0, m1) / (c0 * c1);
+    const float wgt = 1.0f / (float)n_pairs;
+    atomicAdd(loss + t, (1.0f - cosv) * wgt);
+    if (!dverts) return;
+    // d(-cos)/dn0 = -(m1/(c0 c1) - cos * n0 / c0^2)   (norm clamp treated as inactive when l > eps)
+    const f3 g0 = (-wgt) * ((1.f / (c0 * c1)) * m1 - ((l0 > 1e-8f ? cosv / (c0 * c0) : 0.f)) * n0);
+    const f3 g1 = (-wgt) * ((1.f / (c0 * c1)) * n0 - ((l1 > 1e-8f ? cosv / (c1 * c1) : 0.f)) * m1);   // w.r.t. m1 = -n1
+    // n0 = e x ea : de += ea x g0, dea += g0 x e ;  m1 = -(e x eb) : de -= eb x g1, deb -= g1 x e
+    const f3 de = cross(ea, g0) - cross(eb, g1);
+    const f3 dea = cross(g0, e);
+    const f3 deb = mk3(0, 0, 0) - cross(g1, e);
+    const f3 d0 = mk3(0, 0, 0) - (de + dea + deb);
+    float* q0 = dverts + (vb + i0) * 3; float* q1 = dverts + (vb + i1) * 3;
+    float* qa = dverts + (vb + ia) * 3; float* qb = dverts + (vb + ib) * 3;
+    atomicAdd(q0, d0.x); atomicAdd(q0 + 1, d0.y); atomicAdd(q0 + 2, d0.z);
+    atomicAdd(q1, de.x); atomicAdd(q1 + 1, de.y); atomicAdd(q1 + 2, de.z);
+    atomicAdd(qa, dea.x); atomicAdd(qa + 1, dea.y); atomicAdd(qa + 2, dea.z);
+    atomicAdd(qb, deb.x); atomicAdd(qb + 1, deb.y); atomicAdd(qb + 2, deb.z);
+}
+}  // namespace
+
+extern "C" int dm4d_mesh_normal_consistency(const int32_t* pairs, int32_t n_pairs, int32_t n_t, int32_t V,
+                                            const float* verts, float* loss, float* dL_dverts, void* stream) {
+    if (!pairs || !verts || !loss || n_pairs <= 0 || n_t <= 0 || V <= 0) {
+        dm4d_set_error("dm4d_mesh_normal_consistency: bad argument");
+        return DM4D_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    DM4D_CUDA_CHECK(cudaMemsetAsync(loss, 0, (size_t)n_t * sizeof(float), s));
+    if (dL_dverts) DM4D_CUDA_CHECK(cudaMemsetAsync(dL_dverts, 0, (size_t)n_t * V * 3 * sizeof(float), s));
+    const long long n = (long long)n_t * n_pairs;
+    { KernelTimer kt(DM4D_K_NORMAL_CONS, s); normal_consistency_kernel<<<(unsigned)((n + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(pairs, n_pairs, n_t, V, verts, loss, dL_dverts); }
+    DM4D_CUDA_CHECK(cudaGetLastError());
+    return DM4D_OK;
+}

@@ -193,6 +193,13 @@ int dm4d_arap_energy(const float* rest_verts, const int32_t* row_ptr, const int3
                      int32_t n_t, int32_t V, const float* verts, const float* vert_rot, float* energy,
                      float* dE_dverts, float* dE_dvert_rot, void* stream);
 
+/* Mesh normal consistency of the deformed meshes, per timestamp (pytorch3d.loss.mesh_normal_consistency as called at
+ * custom/threestudio-dreammesh4d/system/sugar_4dgen.py:214-225): pairs [n_pairs,4] int32 = (v0, v1, a, b) for every
+ * pair of faces sharing edge (v0,v1) with opposite vertices a and b.  Outputs (overwritten): loss [n_t] (mean over
+ * pairs) and, if non-NULL, d loss_t / d verts [n_t,V,3]. */
+int dm4d_mesh_normal_consistency(const int32_t* pairs, int32_t n_pairs, int32_t n_t, int32_t V, const float* verts,
+                                 float* loss, float* dL_dverts, void* stream);
+
 /* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel launch).
  * Kernel ids: see DM4D_K_* below.  dm4d_profile_collect synchronises the recorded events, ADDS the
  * elapsed milliseconds / launch counts since the last collect into ms[DM4D_K_COUNT] /
@@ -200,7 +207,7 @@ int dm4d_arap_energy(const float* rest_verts, const int32_t* row_ptr, const int3
 enum {
     DM4D_K_PREPROCESS = 0, DM4D_K_SCAN, DM4D_K_SCATTER, DM4D_K_SORT_PACK, DM4D_K_RENDER_FWD,
     DM4D_K_RENDER_BWD, DM4D_K_PREPROCESS_BWD, DM4D_K_SKIN_VERT_FWD, DM4D_K_SKIN_GAUSS_FWD,
-    DM4D_K_SKIN_GAUSS_BWD, DM4D_K_SKIN_VERT_BWD, DM4D_K_REST_FRAMES, DM4D_K_ARAP, DM4D_K_COUNT
+    DM4D_K_SKIN_GAUSS_BWD, DM4D_K_SKIN_VERT_BWD, DM4D_K_REST_FRAMES, DM4D_K_ARAP, DM4D_K_NORMAL_CONS, DM4D_K_COUNT
 };
 int dm4d_profile_enable(int on);
 int dm4d_profile_collect(double* ms_host, int64_t* launches_host);

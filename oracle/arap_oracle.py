@@ -53,3 +53,27 @@ def arap_energy(rest: torch.Tensor, faces: torch.Tensor, verts_t: torch.Tensor, 
         s = ep - q_act(vert_rot_xyzw_t[t][ii], e)
         out.append((w * (s * s).sum(-1)).sum())
     return torch.stack(out)
+
+
+def mesh_normal_consistency(verts_t: torch.Tensor, faces: torch.Tensor) -> torch.Tensor:
+    """pytorch3d.loss.mesh_normal_consistency restated (PARITY UNPINNED: pytorch3d@stable is not installed; call site
+    custom/threestudio-dreammesh4d/system/sugar_4dgen.py:214-225): for every pair of faces sharing an edge (v0,v1)
+    with opposite vertices a, b: n0 = (v1-v0)x(a-v0), n1 = (v1-v0)x(b-v0), term = 1 - cosine_similarity(n0, -n1);
+    mean over pairs per mesh, mean over the batch of meshes.  verts_t [T,V,3]."""
+    from collections import defaultdict
+    edge_faces = defaultdict(list)
+    for fi, f in enumerate(faces.tolist()):
+        for k in range(3):
+            a, b = f[k], f[(k + 1) % 3]
+            edge_faces[(min(a, b), max(a, b))].append(f[(k + 2) % 3])
+    rows = []
+    for (lo, hi), opp in edge_faces.items():
+        for x in range(len(opp)):
+            for y in range(x + 1, len(opp)):
+                rows.append((lo, hi, opp[x], opp[y]))
+    idx = torch.tensor(rows)
+    v0, v1, a, b = (verts_t[:, idx[:, k]] for k in range(4))
+    n0 = torch.cross(v1 - v0, a - v0, dim=-1)
+    n1 = torch.cross(v1 - v0, b - v0, dim=-1)
+    loss = 1 - torch.cosine_similarity(n0, -n1, dim=-1)
+    return loss.mean(dim=1).mean()

@@ -61,3 +61,26 @@ def test_arap_kernel_matches_oracle_energy_and_gradients():
     (e * gE.float().to(dev)).sum().backward()
     assert Hh.rel_linf(xv.grad.cpu().double().numpy(), xp.grad.numpy()) <= Hh.TOL_GRAD
     assert Hh.rel_linf(qv.grad.cpu().double().numpy(), q.grad.numpy()) <= Hh.TOL_GRAD
+
+
+def test_face_pairs_cover_every_interior_edge_once():
+    from dreammesh4d_b200 import synthetic
+    verts, faces = synthetic.uv_sphere(264)
+    pairs = A.face_pairs(faces)
+    assert pairs.shape == (264 * 3 // 2, 4)                 # closed manifold: E = 3F/2 edges, one pair each
+    assert (pairs[:, 0] < pairs[:, 1]).all()
+
+
+@pytest.mark.gpu
+def test_mesh_normal_consistency_kernel_matches_oracle():
+    z = load()
+    dev = "cuda"
+    xp = z["verts_def"].double().requires_grad_(True)
+    ref = AO.mesh_normal_consistency(xp, z["faces"])
+    ref.backward()
+    pairs = A.face_pairs(z["faces"]).to(dev)
+    xv = z["verts_def"].to(dev).requires_grad_(True)
+    got = A.mesh_normal_consistency(xv, pairs)
+    assert abs(float(got) - float(ref)) <= 1e-5 * max(abs(float(ref)), 1e-6) + 1e-7
+    got.backward()
+    assert Hh.rel_linf(xv.grad.cpu().double().numpy(), xp.grad.numpy()) <= Hh.TOL_GRAD
