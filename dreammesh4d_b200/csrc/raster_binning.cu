@@ -9,7 +9,8 @@
 //   3. scatter_kernel: every (view, Gaussian) drops (depth bits << 32 | id) into its tiles' segments,
 //   4. sort_pack_kernel: one CTA per (view, tile) sorts its segment on the full 64-bit key in shared
 //      memory (bitonic network; chunked with global merge steps for segments > 4096) and writes the
-//      depth-sorted instance stream of packed records that the render kernels pull with TMA bulk copies.
+//      depth-sorted instance stream of packed records (with their 4x4-cell masks) that the render kernels pull
+//      with TMA bulk copies.
 // Order = ascending (tile, depth bits, Gaussian id) — exactly the order of upstream's stable radix
 // sort fed in ascending-id emission order, independent of atomics ordering.
 #include "raster_internal.cuh"
@@ -265,10 +266,11 @@ __device__ void smem_merge_sort(unsigned long long* sk, int n) {
 }
 
 // Copies one projected record into the sorted stream, replacing the contribution threshold by the tile-local
-// strip mask: bit s set <=> some pixel of rows (2s, 2s+1) x the tile's 16 columns can reach alpha >= 1/255.
-// Exact ellipse-vs-strip test: the minimum of q(x,y) = cx x^2 + 2 cy x y + cz y^2 (positive definite) over the
-// strip rectangle is 0 if it contains the centre, else it lies on one of the four edges.  Conservative by the
-// margins; never drops a contributing pixel.
+// 16-bit CELL MASK: bit (4 cy + cx) set <=> some pixel of the 4x4 cell (cx, cy) of the tile can reach
+// alpha >= 1/255.  Exact ellipse-vs-rectangle test: the minimum of q(x,y) = cx x^2 + 2 cy x y + cz y^2 (positive
+// definite) over the cell's rectangle is 0 if it contains the centre, else it lies on one of the four edges,
+// where q is a 1-D parabola whose minimiser is clamped to the edge.  Conservative by the margins; never drops a
+// contributing pixel.  The render kernels walk, per half-warp, only the instances whose bit for its cell is set.
 __device__ __forceinline__ void pack_record(const float4* __restrict__ src, float4* __restrict__ dst, int r4,
                                             float tile_x0, float tile_y0) {
     const float4 a = src[0];
@@ -278,25 +280,42 @@ __device__ __forceinline__ void pack_record(const float4* __restrict__ src, floa
     if (thr > 0.f) {
         const float cx = a.z, cy = a.w, cz = b.x;
         if (!(cx > 0.f) || !(cz > 0.f) || !(cx * cz - cy * cy > 0.f) || !(thr < 1e29f)) {
-            mask = 0xffu;
+            mask = 0xffffu;
         } else {
-            const float x0 = tile_x0 - a.x - 0.01f, x1 = tile_x0 + 15.f - a.x + 0.01f;
-            const float icx = 1.f / cx, icz = 1.f / cz;
-            const float yx0 = -cy * x0 * icz, yx1 = -cy * x1 * icz;       // unconstrained minimisers on the edges x = x0, x1
-            const float qx0 = cx * x0 * x0, qx1 = cx * x1 * x1;
-            const bool x_in = x0 <= 0.f && 0.f <= x1;
-            auto qe = [&](float qxx, float x, float y) { return qxx + (2.f * cy * x + cz * y) * y; };
+            const float icx = 1.f / cx, icz = 1.f / cz, cy2 = 2.f * cy;
+            // vertical edges of the four cell columns: x = x0[i], x1[i] (pixel - centre, with margin)
+            float x0[4], x1[4], ys0[4], ys1[4], qx0[4], qx1[4];
+            bool xin[4];
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                const float y0 = tile_y0 + (float)(2 * s) - a.y - 0.01f, y1 = y0 + 1.02f;
-                float qmin = 0.f;
-                if (!(x_in && y0 <= 0.f && 0.f <= y1)) {
-                    const float ya = fminf(fmaxf(yx0, y0), y1), yb = fminf(fmaxf(yx1, y0), y1);
-                    const float xa = fminf(fmaxf(-cy * y0 * icx, x0), x1), xb = fminf(fmaxf(-cy * y1 * icx, x0), x1);
-                    qmin = fminf(fminf(qe(qx0, x0, ya), qe(qx1, x1, yb)),
-                                 fminf(qe(cx * xa * xa, xa, y0), qe(cx * xb * xb, xb, y1)));
+            for (int i = 0; i < 4; ++i) {
+                x0[i] = tile_x0 + (float)(4 * i) - a.x - 0.01f;
+                x1[i] = x0[i] + 3.02f;
+                ys0[i] = -cy * x0[i] * icz;            // unconstrained minimisers along the edges
+                ys1[i] = -cy * x1[i] * icz;
+                qx0[i] = cx * x0[i] * x0[i];
+                qx1[i] = cx * x1[i] * x1[i];
+                xin[i] = x0[i] <= 0.f && 0.f <= x1[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float y0 = tile_y0 + (float)(4 * j) - a.y - 0.01f, y1 = y0 + 3.02f;
+                const float xs0 = -cy * y0 * icx, xs1 = -cy * y1 * icx;
+                const float qy0 = cz * y0 * y0, qy1 = cz * y1 * y1;
+                const bool yin = y0 <= 0.f && 0.f <= y1;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float qmin = 0.f;
+                    if (!(xin[i] && yin)) {
+                        const float ya = fminf(fmaxf(ys0[i], y0), y1), yb = fminf(fmaxf(ys1[i], y0), y1);
+                        const float xa = fminf(fmaxf(xs0, x0[i]), x1[i]), xb = fminf(fmaxf(xs1, x0[i]), x1[i]);
+                        const float qa = qx0[i] + (cy2 * x0[i] + cz * ya) * ya;      // on x = x0
+                        const float qb = qx1[i] + (cy2 * x1[i] + cz * yb) * yb;      // on x = x1
+                        const float qc = qy0 + (cy2 * y0 + cx * xa) * xa;            // on y = y0
+                        const float qd = qy1 + (cy2 * y1 + cx * xb) * xb;            // on y = y1
+                        qmin = fminf(fminf(qa, qb), fminf(qc, qd));
+                    }
+                    if (qmin <= thr) mask |= 1u << (4 * j + i);
                 }
-                if (qmin <= thr) mask |= 1u << s;
             }
         }
     }

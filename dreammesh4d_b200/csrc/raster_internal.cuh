@@ -16,8 +16,8 @@ struct BinHeader {
 //   f[0..3]  = x, y, conic.x, conic.y
 //   f[4..7]  = conic.z, opacity, W, id (int bits)
 //              W = per-Gaussian contribution threshold on the conic quadratic form (geom records), replaced
-//              per (instance, tile) by the 8-bit STRIP MASK (instance stream): bit s set <=> some pixel of the
-//              16x2 strip (rows 2s, 2s+1 of the tile) can reach alpha >= 1/255
+//              per (instance, tile) by the 16-bit CELL MASK (instance stream): bit 4 cy + cx set <=> some pixel of
+//              the 4x4 cell (cx, cy) of the tile can reach alpha >= 1/255
 //   3 ch: f[8..11]  = r, g, b, depth            6 ch: f[8..15] = r, g, b, n0, n1, n2, depth, 0
 __host__ __device__ inline int rec_floats(int channels) { return channels <= 3 ? 12 : 16; }
 __host__ __device__ inline int rec_depth_index(int channels) { return channels <= 3 ? 11 : 14; }

@@ -147,7 +147,7 @@ __device__ __forceinline__ unsigned int preprocess_one(const PreArgs& a, long lo
     // Contribution threshold on the quadratic form q(d) = conic.x dx^2 + 2 conic.y dx dy + conic.z dy^2:
     // alpha = op*exp(-q/2) can reach 1/255 only where q <= 2 ln(255 op).  Stored with a safety margin that
     // covers the render kernels' rounding; <= 0 means the Gaussian can never contribute.  sort_pack turns it
-    // into the per-(instance, tile) strip mask.
+    // into the per-(instance, tile) cell mask.
     float ey = 0.f;
     {
         const float t = logf(255.0f * op);

@@ -6,20 +6,25 @@
 // and alpha outputs.  One CTA per (view, tile), one thread per pixel, all views in one launch.
 //
 // B200 design: the depth-sorted instances of a tile are a contiguous run of packed 48/64-byte
-// records (written by sort_pack_kernel).  Every WARP owns a 16x2 pixel strip and streams the tile's
-// records through its own small shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier
-// complete_tx, issued by the warp's lane 0): warps never meet at a block barrier, so a warp whose strip
-// is light (or saturated) runs ahead / retires while its neighbours keep compositing.  Per group of
-// 32 staged instances the lanes ballot the instances' strip masks and the warp walks only instances
-// that can reach its strip.  The backward walks the same stream back to front, reduces the per-pixel
-// partial gradients across the warp with a 16-shuffle recursive-halving reduction (only when a lane
-// contributes) and issues ONE coalesced 12/16-lane global reduction (RED.ADD.F32) per (warp, instance)
-// instead of upstream's ten global atomics per (pixel, instance).
+// records (written by sort_pack_kernel).  Every WARP owns an 8x4 pixel block made of two 4x4 CELLS, one
+// per HALF-WARP, and streams the tile's records through its own small shared-memory ring with TMA bulk
+// copies (cp.async.bulk + mbarrier complete_tx, issued by the warp's lane 0): warps never meet at a
+// block barrier, so a warp whose block is light (or saturated) runs ahead / retires while its
+// neighbours keep compositing.  Surface-bound Gaussians are tiny (about 10 contributing pixels per
+// (Gaussian, tile) instance at C3), so the unit of culling is the 4x4 cell: per chunk of 64 staged
+// instances the lanes ballot the instances' 16-bit cell masks and each half-warp walks its OWN queue of
+// instances that can reach its cell — the two halves run in lockstep on different instances, which cuts
+// the walked (warp, instance) iterations from 1.91 (16x2 strips) to about 1.2 per instance.  The
+// backward walks the same stream back to front, reduces the per-pixel partial gradients across the 16
+// lanes of the half-warp with a recursive-halving shuffle reduction (11 shuffles for the 10 sums of the
+// 3-channel pass, 15 for 6 channels; only when a lane contributes) and issues ONE coalesced global
+// reduction (RED.ADD.F32, one accumulator row) per (half-warp, instance) instead of upstream's ten
+// global atomics per (pixel, instance).
 #include "raster_internal.cuh"
 
 namespace {
 
-constexpr int THREADS = 256;     // one thread per pixel of a 16x16 tile, 8 warps = 8 strips of 16x2
+constexpr int THREADS = 256;     // one thread per pixel of a 16x16 tile, 8 warps = 8 blocks of 8x4 = 16 cells of 4x4
 constexpr int WARPS = THREADS / 32;
 #ifndef DM4D_WCHUNK
 #define DM4D_WCHUNK 64
@@ -33,6 +38,32 @@ constexpr int WARPS = THREADS / 32;
 constexpr int WCHUNK = DM4D_WCHUNK;     // instances per per-warp stage
 constexpr int WSTAGES = DM4D_WSTAGES;   // per-warp ring depth
 constexpr int FWD_UNROLL = 4;
+static_assert(WCHUNK == 64, "the per-half-warp candidate queue is one 64-bit word per staged chunk");
+
+// Pixel owned by a thread: warp w covers the 8x4 block (w & 1, w >> 1); its half-warp h covers the 4x4 cell
+// (cx, cy) = (2 (w & 1) + h, w >> 1), whose bit in an instance's cell mask is cy * 4 + cx = 2 w + h.
+struct PixelMap {
+    int px, py, cell_bit, half, li;
+    __device__ __forceinline__ PixelMap(int tile_x, int tile_y, int warp, int lane) {
+        half = lane >> 4;
+        li = lane & 15;
+        px = tile_x * DM4D_TILE + (((warp & 1) << 1 | half) << 2) + (li & 3);
+        py = tile_y * DM4D_TILE + ((warp >> 1) << 2) + (li >> 2);
+        cell_bit = 2 * warp + half;
+    }
+};
+
+// Candidate queue of this lane's half-warp for one staged chunk: bit j set <=> instance j of the chunk can reach
+// the half-warp's cell.  Four warp ballots (two cells x two 32-instance groups); uniform within a half-warp.
+template <int R4>
+__device__ __forceinline__ unsigned long long cell_queue(const float4* r, int cnt, int lane, int warp, int half) {
+    const unsigned int m0 = lane < cnt ? __float_as_uint(r[lane * R4 + 1].z) : 0u;
+    const unsigned int m1 = lane + 32 < cnt ? __float_as_uint(r[(lane + 32) * R4 + 1].z) : 0u;
+    const int sh = 2 * warp;
+    const unsigned int a0 = __ballot_sync(0xffffffffu, (m0 >> sh) & 1u), b0 = __ballot_sync(0xffffffffu, (m0 >> (sh + 1)) & 1u);
+    const unsigned int a1 = __ballot_sync(0xffffffffu, (m1 >> sh) & 1u), b1 = __ballot_sync(0xffffffffu, (m1 >> (sh + 1)) & 1u);
+    return half ? (((unsigned long long)b1 << 32) | b0) : (((unsigned long long)a1 << 32) | a0);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -136,10 +167,10 @@ __global__ void __launch_bounds__(THREADS) render_forward_kernel(RasterLayout L,
     const int v = gt / L.tiles, t = gt - v * L.tiles;
     const int tile_x = t % L.gx, tile_y = t / L.gx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int px = tile_x * DM4D_TILE + (tid & 15), py = tile_y * DM4D_TILE + (tid >> 4);
+    const PixelMap pm(tile_x, tile_y, warp, lane);
+    const int px = pm.px, py = pm.py;
     const bool inside = px < L.W && py < L.H;
     const float pfx = (float)px, pfy = (float)py;
-    const unsigned int my_strip = 1u << warp;
 
     const unsigned int beg = L.tile_offset[gt];
     const int n = L.hdr->overflow ? 0 : (int)(L.tile_offset[gt + 1] - beg);
@@ -163,53 +194,51 @@ __global__ void __launch_bounds__(THREADS) render_forward_kernel(RasterLayout L,
             const int slot = c % WSTAGES;
             const float4* r = ring.wait(slot, c / WSTAGES);
             const int cnt = min(WCHUNK, n - c * WCHUNK);
-            for (int g0 = 0; g0 < cnt && !warp_done; g0 += 32) {
-                const int jj = g0 + lane;
-                const unsigned int m = jj < cnt ? __float_as_uint(r[jj * TR::R4 + 1].z) : 0u;
-                unsigned int bal = __ballot_sync(0xffffffffu, (m & my_strip) != 0u);
-                while (bal) {
-                    // Take up to FWD_UNROLL candidates at once: their loads, power and exp are independent,
-                    // only the blend below is sequential.
-                    int js[FWD_UNROLL];
-                    float al[FWD_UNROLL];
+            unsigned long long q = cell_queue<TR::R4>(r, cnt, lane, warp, pm.half);
+            if (done) q = 0ull;
+            while (__any_sync(0xffffffffu, q != 0ull)) {
+                // Take up to FWD_UNROLL candidates of this half-warp's queue at once: their loads, power and exp
+                // are independent, only the blend below is sequential.
+                int js[FWD_UNROLL];
+                float al[FWD_UNROLL];
 #pragma unroll
-                    for (int u = 0; u < FWD_UNROLL; ++u) {
-                        js[u] = bal ? g0 + __ffs(bal) - 1 : -1;
-                        bal &= bal - 1;
-                    }
+                for (int u = 0; u < FWD_UNROLL; ++u) {
+                    js[u] = q ? __ffsll((long long)q) - 1 : -1;
+                    q &= q - 1ull;
+                }
 #pragma unroll
-                    for (int u = 0; u < FWD_UNROLL; ++u) {
-                        al[u] = 0.f;
-                        if (js[u] >= 0 && !done) {
-                            const float4* rp = r + js[u] * TR::R4;
-                            const float4 a = rp[0];
-                            const float4 b = rp[1];
-                            const float dx = a.x - pfx, dy = a.y - pfy;
-                            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-                            const float alpha = fminf(0.99f, b.y * expf(power));
-                            al[u] = (power > 0.0f || alpha < 1.0f / 255.0f) ? 0.f : alpha;
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < FWD_UNROLL; ++u) {
-                        if (al[u] > 0.f && !done) {
-                            const float alpha = al[u];
-                            const float test_T = T * (1.0f - alpha);
-                            if (test_T < 0.0001f) { done = true; continue; }
-                            float f[C], dep;
-                            load_features<C>(r + js[u] * TR::R4, f, dep);
-                            const float w = alpha * T;
-#pragma unroll
-                            for (int ch = 0; ch < C; ++ch) Cacc[ch] += f[ch] * w;
-                            D += dep * w;
-                            Wg += w;
-                            T = test_T;
-                            last = (unsigned int)(c * WCHUNK + js[u] + 1);
-                        }
+                for (int u = 0; u < FWD_UNROLL; ++u) {
+                    al[u] = 0.f;
+                    if (js[u] >= 0 && !done) {
+                        const float4* rp = r + js[u] * TR::R4;
+                        const float4 a = rp[0];
+                        const float4 b = rp[1];
+                        const float dx = a.x - pfx, dy = a.y - pfy;
+                        const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+                        const float alpha = fminf(0.99f, b.y * expf(power));
+                        al[u] = (power > 0.0f || alpha < 1.0f / 255.0f) ? 0.f : alpha;
                     }
                 }
-                warp_done = __all_sync(0xffffffffu, done);
+#pragma unroll
+                for (int u = 0; u < FWD_UNROLL; ++u) {
+                    if (al[u] > 0.f && !done) {
+                        const float alpha = al[u];
+                        const float test_T = T * (1.0f - alpha);
+                        if (test_T < 0.0001f) { done = true; continue; }
+                        float f[C], dep;
+                        load_features<C>(r + js[u] * TR::R4, f, dep);
+                        const float w = alpha * T;
+#pragma unroll
+                        for (int ch = 0; ch < C; ++ch) Cacc[ch] += f[ch] * w;
+                        D += dep * w;
+                        Wg += w;
+                        T = test_T;
+                        last = (unsigned int)(c * WCHUNK + js[u] + 1);
+                    }
+                }
+                if (done) q = 0ull;
             }
+            warp_done = __all_sync(0xffffffffu, done);
             __syncwarp();
             if (warp_done) break;
             if (lane == 0 && c + WSTAGES < nchunks) ring.issue(c + WSTAGES, slot);
@@ -234,29 +263,60 @@ __global__ void __launch_bounds__(THREADS) render_forward_kernel(RasterLayout L,
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-// Sums 16 per-lane values across the warp with 16 shuffles (recursive halving): after the call the
-// lane pair (2k, 2k+1) holds the warp total of slot k.
-__device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane) {
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+// Recursive-halving reductions over the 16 lanes of a half-warp (xor distances 8, 4, 2, 1 never leave the half).
+// After the call lane `li` holds the half-warp total of ONE slot; `slot_of` gives that slot (or -1 for idle lanes).
+//
+// N = 16 slots: 8 + 4 + 2 + 1 = 15 shuffles, lane li ends with slot li.
+__device__ __forceinline__ float half_reduce_scatter16(float (&v)[16], int li) {
+    const bool b3 = li & 8, b2 = li & 4, b1 = li & 2, b0 = li & 1;
     float w8[8], w4[4], w2[2];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float send = b4 ? v[i] : v[i + 8], keep = b4 ? v[i + 8] : v[i];
-        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        const float send = b3 ? v[i] : v[i + 8], keep = b3 ? v[i + 8] : v[i];
+        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float send = b3 ? w8[i] : w8[i + 4], keep = b3 ? w8[i + 4] : w8[i];
-        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        const float send = b2 ? w8[i] : w8[i + 4], keep = b2 ? w8[i + 4] : w8[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const float send = b2 ? w4[i] : w4[i + 2], keep = b2 ? w4[i + 2] : w4[i];
-        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        const float send = b1 ? w4[i] : w4[i + 2], keep = b1 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
     }
-    const float send = b1 ? w2[0] : w2[1], keep = b1 ? w2[1] : w2[0];
-    const float w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    return w1 + __shfl_xor_sync(0xffffffffu, w1, 1);
+    const float send = b0 ? w2[0] : w2[1], keep = b0 ? w2[1] : w2[0];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+// N = 10 slots (the 3-channel pass: 2 dmean2D, 3 dconic, dopacity, ddepth, 3 dfeatures): 10 -> 5 -> 3 -> 2 -> 1 with
+// 5 + 3 + 2 + 1 = 11 shuffles.  Lane li ends with slot 5*b3 + 3*b2 + (2*b1 + b0) when 2*b1 + b0 <= 2 and
+// 3*b2 + 2*b1 + b0 <= 4; the other six lanes of the half hold padding.
+__device__ __forceinline__ float half_reduce_scatter10(float (&v)[10], int li) {
+    const bool b3 = li & 8, b2 = li & 4, b1 = li & 2, b0 = li & 1;
+    float w[6], x[4], y[2];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float send = b3 ? v[i] : v[i + 5], keep = b3 ? v[i + 5] : v[i];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    w[5] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float send = b2 ? w[i] : w[i + 3], keep = b2 ? w[i + 3] : w[i];
+        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    x[3] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b1 ? x[i] : x[i + 2], keep = b1 ? x[i + 2] : x[i];
+        y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const float send = b0 ? y[0] : y[1], keep = b0 ? y[1] : y[0];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+__device__ __forceinline__ int slot_of10(int li) {
+    const int t = li & 3, u = ((li & 4) ? 3 : 0) + t;
+    return (t <= 2 && u <= 4) ? ((li & 8) ? 5 : 0) + u : -1;
 }
 
 template <int C>
@@ -272,12 +332,12 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
     const int v = gt / L.tiles, t = gt - v * L.tiles;
     const int tile_x = t % L.gx, tile_y = t / L.gx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int px = tile_x * DM4D_TILE + (tid & 15), py = tile_y * DM4D_TILE + (tid >> 4);
+    const PixelMap pm(tile_x, tile_y, warp, lane);
+    const int px = pm.px, py = pm.py;
     const bool inside = px < L.W && py < L.H;
     const float pfx = (float)px, pfy = (float)py;
     const size_t npix = (size_t)L.H * L.W;
     const size_t pix = (size_t)py * L.W + px;
-    const unsigned int my_strip = 1u << warp;
 
     const unsigned int beg = L.tile_offset[gt];
     const int n = L.hdr->overflow ? 0 : (int)(L.tile_offset[gt + 1] - beg);
@@ -287,7 +347,7 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
     unsigned int warp_last = last_contributor;      // last contributor over the warp's 32 pixels
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
-    if (warp_last == 0) return;                      // nothing composited in this strip
+    if (warp_last == 0) return;                      // nothing composited in this block
     const int nlive = min(n, (int)warp_last);        // this warp only needs instances in front of its last contributor
     const int nchunks = (nlive + WCHUNK - 1) / WCHUNK;
 
@@ -315,84 +375,96 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
     float accum_d = 0.f, last_depth = 0.f, accum_a = 0.f, last_alpha = 0.f;
     const float ddelx_dx = 0.5f * (float)L.W, ddely_dy = 0.5f * (float)L.H;
     float* accum_view = L.accum + (size_t)v * L.P * TR::ACC;
-    const int slot = lane >> 1;
-    const bool writer = !(lane & 1) && slot < TR::ACC && slot != 7;
+    // accumulator-row offset this lane adds its reduced slot to (rows: raster_internal.cuh); -1 = idle lane
+    int acc_off;
+    if constexpr (C <= 3) {
+        const int sl = slot_of10(pm.li);          // reduction slots 0..6 = row 0..6, slots 7..9 = features at row 8..10
+        acc_off = sl < 0 ? -1 : (sl < 7 ? sl : sl + 1);
+    } else {
+        acc_off = (pm.li != 7 && pm.li < 8 + C) ? pm.li : -1;
+    }
+    const unsigned int half_lanes = 0xffffu << (pm.half * 16);
 
     for (int k = 0; k < nchunks; ++k) {
         const int c = nchunks - 1 - k;
         const int sl = k % WSTAGES;
         const float4* r = ring.wait(sl, k / WSTAGES);
         const int cnt = min(WCHUNK, nlive - c * WCHUNK);
-        for (int g0 = (cnt - 1) & ~31; g0 >= 0; g0 -= 32) {
-            const int jj = g0 + lane;
-            const unsigned int m = jj < cnt ? __float_as_uint(r[jj * TR::R4 + 1].z) : 0u;
-            unsigned int bal = __ballot_sync(0xffffffffu, (m & my_strip) != 0u);
-            while (bal) {
-                const int bpos = 31 - __clz(bal);
-                bal &= ~(1u << bpos);
-                const int j = g0 + bpos;
-                const unsigned int gi = (unsigned int)(c * WCHUNK + j);
-                const float4* rp = r + j * TR::R4;
-                bool valid = gi < last_contributor;
-                float4 a, b;
-                float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
+        unsigned long long q = cell_queue<TR::R4>(r, cnt, lane, warp, pm.half);
+        while (__any_sync(0xffffffffu, q != 0ull)) {
+            // next instance of this half-warp's queue, back to front (the two halves walk different instances)
+            const bool have = q != 0ull;
+            const int j = have ? 63 - __clzll((long long)q) : 0;
+            q &= ~(1ull << j);
+            const unsigned int gi = (unsigned int)(c * WCHUNK + j);
+            const float4* rp = r + j * TR::R4;
+            bool valid = have && gi < last_contributor;
+            float4 a, b;
+            float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
+            if (valid) {
+                a = rp[0];
+                b = rp[1];
+                dx = a.x - pfx; dy = a.y - pfy;
+                const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+                valid = !(power > 0.0f);
                 if (valid) {
-                    a = rp[0];
-                    b = rp[1];
-                    dx = a.x - pfx; dy = a.y - pfy;
-                    const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-                    valid = !(power > 0.0f);
-                    if (valid) {
-                        G = expf(power);
-                        alpha = fminf(0.99f, b.y * G);
-                        valid = !(alpha < 1.0f / 255.0f);
-                    }
+                    G = expf(power);
+                    alpha = fminf(0.99f, b.y * G);
+                    valid = !(alpha < 1.0f / 255.0f);
                 }
-                if (!__any_sync(0xffffffffu, valid)) continue;
+            }
+            const unsigned int vb = __ballot_sync(0xffffffffu, valid);
+            if (vb == 0u) continue;
 
-                // slots: 0-1 dmean2D, 2-4 dconic, 5 dopacity, 6 ddepth, 7 unused, 8.. dfeatures
-                float gv[16];
+            // reduction slots: 0-1 dmean2D, 2-4 dconic, 5 dopacity, 6 ddepth, then the C feature gradients
+            // (3 channels: slots 7..9 of a 10-slot reduction; 6 channels: slots 8..13 of a 16-slot one, 7 unused)
+            constexpr int NS = C <= 3 ? 10 : 16;
+            constexpr int F0 = C <= 3 ? 7 : 8;
+            float gv[NS];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) gv[i] = 0.f;
-                if (valid) {
-                    const float inv_1ma = __frcp_rn(1.0f - alpha);     // shared by both uses below (1 ulp)
-                    T = T * inv_1ma;
-                    const float w = alpha * T;
-                    float f[C], dep;
-                    load_features<C>(rp, f, dep);
-                    float dL_dalpha = 0.f;
+            for (int i = 0; i < NS; ++i) gv[i] = 0.f;
+            if (valid) {
+                const float inv_1ma = __frcp_rn(1.0f - alpha);     // shared by both uses below (1 ulp)
+                T = T * inv_1ma;
+                const float w = alpha * T;
+                float f[C], dep;
+                load_features<C>(rp, f, dep);
+                float dL_dalpha = 0.f;
 #pragma unroll
-                    for (int ch = 0; ch < C; ++ch) {
-                        accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                        last_color[ch] = f[ch];
-                        dL_dalpha += (f[ch] - accum_rec[ch]) * gC[ch];
-                        gv[8 + ch] = w * gC[ch];
-                    }
-                    accum_d = last_alpha * last_depth + (1.f - last_alpha) * accum_d;
-                    last_depth = dep;
-                    dL_dalpha += (dep - accum_d) * gD;
-                    gv[6] = w * gD;
-                    accum_a = last_alpha + (1.f - last_alpha) * accum_a;
-                    dL_dalpha += (1.f - accum_a) * gA;
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final * inv_1ma) * bg_dot;
-                    const float dL_dG = b.y * dL_dalpha;
-                    const float gdx = G * dx, gdy = G * dy;
-                    const float dG_ddelx = -gdx * a.z - gdy * a.w;
-                    const float dG_ddely = -gdy * b.x - gdx * a.w;
-                    gv[0] = dL_dG * dG_ddelx * ddelx_dx;
-                    gv[1] = dL_dG * dG_ddely * ddely_dy;
-                    const float hx = -0.5f * dL_dG * gdx, hy = -0.5f * dL_dG * gdy;   // shared factors of the conic terms
-                    gv[2] = hx * dx;
-                    gv[3] = hx * dy;
-                    gv[4] = hy * dy;
-                    gv[5] = G * dL_dalpha;
+                for (int ch = 0; ch < C; ++ch) {
+                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                    last_color[ch] = f[ch];
+                    dL_dalpha += (f[ch] - accum_rec[ch]) * gC[ch];
+                    gv[F0 + ch] = w * gC[ch];
                 }
-                const float tot = warp_reduce_scatter16(gv, lane);
-                // one coalesced reduction per (warp, instance): lanes 0,2,4,.. add slot 0,1,2,.. of the instance's row
+                accum_d = last_alpha * last_depth + (1.f - last_alpha) * accum_d;
+                last_depth = dep;
+                dL_dalpha += (dep - accum_d) * gD;
+                gv[6] = w * gD;
+                accum_a = last_alpha + (1.f - last_alpha) * accum_a;
+                dL_dalpha += (1.f - accum_a) * gA;
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final * inv_1ma) * bg_dot;
+                const float dL_dG = b.y * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * a.z - gdy * a.w;
+                const float dG_ddely = -gdy * b.x - gdx * a.w;
+                gv[0] = dL_dG * dG_ddelx * ddelx_dx;
+                gv[1] = dL_dG * dG_ddely * ddely_dy;
+                const float hx = -0.5f * dL_dG * gdx, hy = -0.5f * dL_dG * gdy;   // shared factors of the conic terms
+                gv[2] = hx * dx;
+                gv[3] = hx * dy;
+                gv[4] = hy * dy;
+                gv[5] = G * dL_dalpha;
+            }
+            float tot;
+            if constexpr (C <= 3) tot = half_reduce_scatter10(gv, pm.li);
+            else tot = half_reduce_scatter16(gv, pm.li);
+            // one coalesced reduction per (half-warp, instance) into the instance's accumulator row
+            if (acc_off >= 0 && (vb & half_lanes)) {
                 const int id = __float_as_int(rp[1].w);
-                if (writer) atomicAdd(accum_view + (size_t)id * TR::ACC + slot, tot);
+                atomicAdd(accum_view + (size_t)id * TR::ACC + acc_off, tot);
             }
         }
         __syncwarp();

@@ -26,10 +26,11 @@ def run_oracle(P, H, W, means, scales, rots, opac, cols, V, PV, tanx, tany, bg, 
     return o
 
 
-def check_view(o: RasterOracle, color, radii, depth, alpha, state, view, check_state=True):
+def check_view(o: RasterOracle, color, radii, depth, alpha, state, view, check_state=True,
+               max_ambig=MAX_AMBIG_FRACTION):
     amb = o.ambiguous
     ok = ~amb
-    assert amb.mean() <= MAX_AMBIG_FRACTION, f"too many ambiguous pixels: {amb.mean()}"
+    assert amb.mean() <= max_ambig, f"too many ambiguous pixels: {amb.mean()}"
     np.testing.assert_array_equal(radii.cpu().numpy(), o.radii)
     if check_state:
         ranges, pl, nc = state.export_view(view)
