@@ -6,11 +6,13 @@ fails loudly.
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint32, c_uint64, c_void_p
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libdm4d.so"
+# DM4D_LIB_PATH selects another build of the same library (kernel-tuning variants, scripts/tune_variants.sh)
+LIB_PATH = Path(os.environ["DM4D_LIB_PATH"]) if os.environ.get("DM4D_LIB_PATH") else PKG / "lib" / "libdm4d.so"
 
 DM4D_VIEW_STRIDE = 48
 VIEW_TANFOVX, VIEW_TANFOVY, VIEW_SCALE_MOD, VIEW_SET, VIEW_BG = 35, 36, 37, 38, 40
@@ -48,6 +50,22 @@ class SkinDesc(ctypes.Structure):
     ]
 
 
+class PostopsDesc(ctypes.Structure):
+    """Mirror of ``dm4d_postops_desc`` (include/dm4d.h)."""
+    _fields_ = [("n_views", c_int32), ("H", c_int32), ("W", c_int32), ("flags", c_int32),
+                ("color6", c_void_p), ("depth", c_void_p), ("alpha", c_void_p), ("rays_o", c_void_p), ("rays_d", c_void_p)]
+
+
+POSTOPS_NORMAL_FROM_DIST, POSTOPS_STATIC = 1, 2
+HEX_MAX_SCALES = 8
+
+
+class HexplaneDesc(ctypes.Structure):
+    """Mirror of ``dm4d_hexplane_desc`` (include/dm4d.h)."""
+    _fields_ = [("n_points", c_int32), ("n_scales", c_int32), ("feat", c_int32), ("reserved", c_int32),
+                ("coords", c_void_p), ("planes", (c_void_p * 6) * HEX_MAX_SCALES), ("res", (c_int32 * 4) * HEX_MAX_SCALES)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/dm4d.h
 SIGNATURES = {
     "dm4d_raster_workspace_bytes": (ctypes.c_int, [c_int32] * 5 + [c_int64] + [POINTER(c_uint64)] * 4),
@@ -63,6 +81,10 @@ SIGNATURES = {
     "dm4d_sugar_rest_frames_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dm4d_arap_energy": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dm4d_mesh_normal_consistency": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dm4d_postops_forward": (ctypes.c_int, [POINTER(PostopsDesc)] + [c_void_p] * 6),
+    "dm4d_postops_backward": (ctypes.c_int, [POINTER(PostopsDesc)] + [c_void_p] * 10),
+    "dm4d_hexplane_forward": (ctypes.c_int, [POINTER(HexplaneDesc), c_void_p, c_void_p]),
+    "dm4d_hexplane_backward": (ctypes.c_int, [POINTER(HexplaneDesc), c_void_p, POINTER(c_void_p), c_void_p]),
     "dm4d_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "dm4d_profile_collect": (ctypes.c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
     "dm4d_kernel_name": (c_char_p, [ctypes.c_int]),
@@ -70,7 +92,7 @@ SIGNATURES = {
     "dm4d_version": (ctypes.c_int, []),
 }
 
-K_COUNT = 14
+K_COUNT = 18
 
 _lib = None
 

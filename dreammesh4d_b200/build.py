@@ -26,6 +26,8 @@ UNITS = {
     "raster_binning.cu": [],
     "raster_render.cu": [],
     "skin.cu": [],
+    "postops.cu": [],
+    "hexplane.cu": [],
     "capi.cu": [],
 }
 
@@ -49,18 +51,21 @@ def is_stale() -> bool:
     return any(p.stat().st_mtime > t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out: Path | None = None, extra: str | None = None) -> Path:
+    """``out`` / ``extra``: build a tuning variant (extra nvcc flags) into another file, leaving LIB untouched."""
+    if out is None and not force and not is_stale():
         return LIB
     nvcc = _nvcc()
     LIBDIR.mkdir(exist_ok=True)
-    objdir = PKG / "build"
-    objdir.mkdir(exist_ok=True)
+    objdir = PKG / "build" / (out.stem if out is not None else "default")
+    objdir.mkdir(parents=True, exist_ok=True)
+    target = out if out is not None else LIB
+    extra_flags = (extra if extra is not None else os.environ.get("DM4D_NVCC_EXTRA", "")).split()
     host_cc = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else None
 
     def compile_one(src: Path) -> Path:
         obj = objdir / (src.stem + ".o")
-        cmd = [nvcc, *ARCH, *COMMON, *UNITS[src.name], *os.environ.get("DM4D_NVCC_EXTRA", "").split(), "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *ARCH, *COMMON, *UNITS[src.name], *extra_flags, "-c", str(src), "-o", str(obj)]
         if host_cc:
             cmd[1:1] = ["-ccbin", host_cc]
         if verbose:
@@ -74,14 +79,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [nvcc, *ARCH, "-shared", "-o", str(LIB), *map(str, objs)]
+    cmd = [nvcc, *ARCH, "-shared", "-o", str(target), *map(str, objs)]
     if host_cc:
         cmd[1:1] = ["-ccbin", host_cc]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

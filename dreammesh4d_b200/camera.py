@@ -9,8 +9,11 @@ import torch
 
 def convert_pose(c2w: torch.Tensor) -> torch.Tensor:
     """ops.py:359-364 — flip the camera y and z axes (OpenGL -> COLMAP convention)."""
-    flip = torch.tensor([1.0, -1.0, -1.0, 1.0], dtype=c2w.dtype, device=c2w.device)
-    return c2w * flip          # right-multiplication by diag(1,-1,-1,1) scales the columns
+    # right-multiplication by diag(1,-1,-1,1) scales the columns; built from device-side ops only (no pageable
+    # host->device copy, which would synchronise and cannot be captured into a CUDA graph)
+    flip = torch.ones(4, dtype=c2w.dtype, device=c2w.device)
+    flip[1:3] = -1.0
+    return c2w * flip
 
 
 def get_projection_matrix_gaussian(znear: float, zfar: float, tan_half_fovx: torch.Tensor,
@@ -34,10 +37,11 @@ def get_cam_info_gaussian(c2w: torch.Tensor, fovx: torch.Tensor, fovy: torch.Ten
     (world_view_transform [B,4,4] transposed, full_proj_transform [B,4,4] transposed,
     camera_center [B,3], tanfovx [B], tanfovy [B])."""
     c2w = convert_pose(c2w.float())
-    w2c = torch.linalg.inv(c2w)
+    # inv_ex: same LU-based inverse as torch.inverse (ops.py:400) without the host-synchronising error check
+    w2c = torch.linalg.inv_ex(c2w).inverse
     world_view = w2c.transpose(1, 2).contiguous()
     tanx, tany = torch.tan(fovx.float() * 0.5), torch.tan(fovy.float() * 0.5)
     proj = get_projection_matrix_gaussian(znear, zfar, tanx, tany).transpose(1, 2)
     full = torch.bmm(world_view, proj)
-    center = torch.linalg.inv(world_view)[:, 3, :3]
+    center = torch.linalg.inv_ex(world_view).inverse[:, 3, :3]
     return world_view, full, center, tanx, tany

@@ -24,21 +24,44 @@
 
 namespace {
 
-constexpr int THREADS = 256;     // one thread per pixel of a 16x16 tile, 8 warps = 8 blocks of 8x4 = 16 cells of 4x4
-constexpr int WARPS = THREADS / 32;
+// One thread per pixel of a 16x16 tile: 8 warps = 8 blocks of 8x4 = 16 cells of 4x4.  The warps of a tile never
+// synchronise, so a tile may be split over PARTS CTAs of RWARPS warps each: smaller CTAs free their SM slot as soon
+// as their own warps retire instead of waiting for the slowest block of the tile (measured at C3, step time:
+// 8 warps 2.42 ms, 4: 2.32, 2: 2.32, 1: 2.26 -> one warp per CTA).
+#ifndef DM4D_RENDER_WARPS
+#define DM4D_RENDER_WARPS 1
+#endif
+constexpr int WARPS = DM4D_RENDER_WARPS;      // warps per CTA
+constexpr int THREADS = 32 * WARPS;
+constexpr int PARTS = 8 / WARPS;              // CTAs per tile
+static_assert(WARPS == 1 || WARPS == 2 || WARPS == 4 || WARPS == 8, "DM4D_RENDER_WARPS must divide 8");
 #ifndef DM4D_WCHUNK
 #define DM4D_WCHUNK 64
 #endif
 #ifndef DM4D_WSTAGES
 #define DM4D_WSTAGES 2
 #endif
-#ifndef DM4D_BWD_MIN_BLOCKS
-#define DM4D_BWD_MIN_BLOCKS 4
+#ifndef DM4D_BWD_MIN_WARPS
+#define DM4D_BWD_MIN_WARPS 32     // resident warps per SM the backward's register budget is sized for
 #endif
+#define DM4D_BWD_MIN_BLOCKS (DM4D_BWD_MIN_WARPS / DM4D_RENDER_WARPS)
 constexpr int WCHUNK = DM4D_WCHUNK;     // instances per per-warp stage
 constexpr int WSTAGES = DM4D_WSTAGES;   // per-warp ring depth
-constexpr int FWD_UNROLL = 4;
+#ifndef DM4D_FWD_UNROLL
+#define DM4D_FWD_UNROLL 4
+#endif
+constexpr int FWD_UNROLL = DM4D_FWD_UNROLL;
 static_assert(WCHUNK == 64, "the per-half-warp candidate queue is one 64-bit word per staged chunk");
+
+// exp of the (non-positive, >= -5.6 where it matters) Gaussian exponent: ex2.approx(x * log2 e), 2 instructions
+// instead of expf's 10; relative error < 5e-7, far inside the image tolerance and the parity tests' threshold-ambiguity
+// margin (2e-5).  Forward and backward use the same function, so their contribution decisions agree bit for bit.
+__device__ __forceinline__ float gauss_exp(float x) { return __expf(x); }
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 // Pixel owned by a thread: warp w covers the 8x4 block (w & 1, w >> 1); its half-warp h covers the 4x4 cell
 // (cx, cy) = (2 (w & 1) + h, w >> 1), whose bit in an instance's cell mask is cy * 4 + cx = 2 w + h.
@@ -163,10 +186,11 @@ __global__ void __launch_bounds__(THREADS) render_forward_kernel(RasterLayout L,
     using TR = RecTraits<C>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
-    const int gt = (int)L.tile_order[blockIdx.x];
+    const int gt = (int)L.tile_order[blockIdx.x / PARTS];
     const int v = gt / L.tiles, t = gt - v * L.tiles;
     const int tile_x = t % L.gx, tile_y = t / L.gx;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wl = tid >> 5;     // wl: warp within the CTA (ring slot)
+    const int warp = (int)(blockIdx.x % PARTS) * WARPS + wl;          // warp within the tile (pixel block)
     const PixelMap pm(tile_x, tile_y, warp, lane);
     const int px = pm.px, py = pm.py;
     const bool inside = px < L.W && py < L.H;
@@ -186,7 +210,7 @@ __global__ void __launch_bounds__(THREADS) render_forward_kernel(RasterLayout L,
 
     if (!warp_done && nchunks > 0) {
         WarpRing<C> ring;
-        ring.init(smem_raw, warp, lane, L.stream + (size_t)beg * TR::REC, n);
+        ring.init(smem_raw, wl, lane, L.stream + (size_t)beg * TR::REC, n);
         if (lane == 0)
             for (int c = 0; c < min(WSTAGES, nchunks); ++c) ring.issue(c, c);
         int c = 0;
@@ -215,7 +239,7 @@ __global__ void __launch_bounds__(THREADS) render_forward_kernel(RasterLayout L,
                         const float4 b = rp[1];
                         const float dx = a.x - pfx, dy = a.y - pfy;
                         const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-                        const float alpha = fminf(0.99f, b.y * expf(power));
+                        const float alpha = fminf(0.99f, b.y * gauss_exp(power));
                         al[u] = (power > 0.0f || alpha < 1.0f / 255.0f) ? 0.f : alpha;
                     }
                 }
@@ -328,10 +352,11 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
     using TR = RecTraits<C>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
-    const int gt = (int)L.tile_order[blockIdx.x];
+    const int gt = (int)L.tile_order[blockIdx.x / PARTS];
     const int v = gt / L.tiles, t = gt - v * L.tiles;
     const int tile_x = t % L.gx, tile_y = t / L.gx;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wl = tid >> 5;     // wl: warp within the CTA (ring slot)
+    const int warp = (int)(blockIdx.x % PARTS) * WARPS + wl;          // warp within the tile (pixel block)
     const PixelMap pm(tile_x, tile_y, warp, lane);
     const int px = pm.px, py = pm.py;
     const bool inside = px < L.W && py < L.H;
@@ -352,7 +377,7 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
     const int nchunks = (nlive + WCHUNK - 1) / WCHUNK;
 
     WarpRing<C> ring;
-    ring.init(smem_raw, warp, lane, L.stream + (size_t)beg * TR::REC, nlive);
+    ring.init(smem_raw, wl, lane, L.stream + (size_t)beg * TR::REC, nlive);
     // k-th chunk in processing order = chunk index nchunks-1-k (back to front)
     if (lane == 0)
         for (int k = 0; k < min(WSTAGES, nchunks); ++k) ring.issue(nchunks - 1 - k, k);
@@ -408,7 +433,7 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
                 const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
                 valid = !(power > 0.0f);
                 if (valid) {
-                    G = expf(power);
+                    G = gauss_exp(power);
                     alpha = fminf(0.99f, b.y * G);
                     valid = !(alpha < 1.0f / 255.0f);
                 }
@@ -424,7 +449,7 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
 #pragma unroll
             for (int i = 0; i < NS; ++i) gv[i] = 0.f;
             if (valid) {
-                const float inv_1ma = __frcp_rn(1.0f - alpha);     // shared by both uses below (1 ulp)
+                const float inv_1ma = fast_rcp(1.0f - alpha);       // MUFU.RCP (1 ulp), shared by both uses below
                 T = T * inv_1ma;
                 const float w = alpha * T;
                 float f[C], dep;
@@ -483,7 +508,7 @@ int launch_fwd_t(const dm4d_raster_desc* d, const RasterLayout& L, float* out_co
     }
     {
         KernelTimer kt(DM4D_K_RENDER_FWD, s);
-        render_forward_kernel<C><<<(unsigned)(L.n_views * L.tiles), THREADS, smem, s>>>(L, d->view_params, out_color,
+        render_forward_kernel<C><<<(unsigned)(L.n_views * L.tiles * PARTS), THREADS, smem, s>>>(L, d->view_params, out_color,
                                                                                         out_depth, out_alpha);
     }
     DM4D_CUDA_CHECK(cudaGetLastError());
@@ -502,7 +527,7 @@ int launch_bwd_t(const dm4d_raster_desc* d, const RasterLayout& L, const float* 
     DM4D_CUDA_CHECK(cudaMemsetAsync(L.accum, 0, (size_t)L.n_views * L.P * L.acc * sizeof(float), s));
     {
         KernelTimer kt(DM4D_K_RENDER_BWD, s);
-        render_backward_kernel<C><<<(unsigned)(L.n_views * L.tiles), THREADS, smem, s>>>(L, d->view_params, out_alpha,
+        render_backward_kernel<C><<<(unsigned)(L.n_views * L.tiles * PARTS), THREADS, smem, s>>>(L, d->view_params, out_alpha,
                                                                                          dL_dcolor, dL_ddepth, dL_dalpha);
     }
     DM4D_CUDA_CHECK(cudaGetLastError());

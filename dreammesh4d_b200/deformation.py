@@ -1,5 +1,9 @@
-"""HexPlane + MLP deformation network (row A1 of SURVEY.md §8a) — kept in PyTorch by the north-star:
-M <= 1000 query points per timestamp, launch-latency bound, feeds the fused skinning kernel.
+"""HexPlane + MLP deformation network (row A1 of SURVEY.md §8a): M <= 1000 query points per timestamp,
+launch-latency bound, feeds the fused skinning kernel.  The plane lookup (6 planes x 4 scales of bilinear samples,
+their products and the concatenation) runs as ONE fused kernel each way (``hexplane.py`` -> dm4d_hexplane_*,
+row (f)3); the small MLP heads stay PyTorch tensor-core matmuls, as the north-star prescribes for A1.
+``fused=False`` evaluates the lookup with F.grid_sample exactly like the reference (used by tests as the PyTorch
+statement of A1 and for CPU tensors); on CUDA the default is the fused kernel and nothing falls back silently.
 
 Own implementation of the network the reference builds in
 custom/threestudio-dreammesh4d/geometry/deformation.py (HexPlaneField :177-248, interpolate_ms_features
@@ -20,8 +24,9 @@ PLANES = list(itertools.combinations(range(4), 2))      # (x,y) (x,z) (x,t) (y,z
 
 
 class _HexPlanes(nn.Module):
-    def __init__(self, bounds=1.0, feat=32, base_res=(64, 64, 64, 25), multires=(1, 2, 4, 8)):
+    def __init__(self, bounds=1.0, feat=32, base_res=(64, 64, 64, 25), multires=(1, 2, 4, 8), fused=True):
         super().__init__()
+        self.fused = fused
         self.aabb = nn.Parameter(torch.tensor([[bounds] * 3, [-bounds] * 3]), requires_grad=False)
         self.grids = nn.ModuleList()
         for m in multires:
@@ -41,6 +46,9 @@ class _HexPlanes(nn.Module):
         """pts [N,3], t [N,1] -> [N, feat_dim]."""
         p = (pts - self.aabb[0]) * (2.0 / (self.aabb[1] - self.aabb[0])) - 1.0
         q = torch.cat([p, t], dim=-1)
+        if self.fused:
+            from .hexplane import hexplane_features
+            return hexplane_features(q, [list(planes) for planes in self.grids])
         feats = []
         for planes in self.grids:
             prod = 1.0
@@ -86,6 +94,7 @@ class HexPlaneDeformation(nn.Module):
     opacity_delta [T,M,1] | None)``; timestamps in (0,1) are mapped to 2t-1 (dynamic_sugar.py:431)."""
 
     def __init__(self, width=64, no_ds=False, no_do=False, timebase_pe=4, timenet_width=64, timenet_output=32, **grid_kw):
+        """``grid_kw``: bounds, feat, base_res, multires, fused (see _HexPlanes)."""
         super().__init__()
         self.timenet = nn.Sequential(nn.Linear(2 * timebase_pe + 1, timenet_width), nn.ReLU(),
                                      nn.Linear(timenet_width, timenet_output))     # present but unused, as in the reference

@@ -6,32 +6,18 @@ GaussianBatchRenderer.batch_forward + DiffGaussian.forward
 renderer/diff_sugar_rasterizer_temporal.py:81-239) but renders every view of the batch in ONE launch
 sequence: batched camera matrices, one fused skinning call for all timestamps, one 6-channel rasterizer
 call (RGB + per-Gaussian normals share projection, binning and sort), no per-view host synchronisation
-(no ``.item()``, no boolean-mask indexing).
+(no ``.item()``, no boolean-mask indexing) and one fused post-op kernel (``postops.py``) for the image tail.
 """
 from __future__ import annotations
 
 from typing import Any, Dict, Optional
 
 import torch
-import torch.nn.functional as F
 
 from . import rasterizer as R
+from .postops import post_ops
 from .camera import get_cam_info_gaussian
 from .geometry import DynamicSuGaRGeometry
-
-
-def depth_to_normal(xyz_map: torch.Tensor) -> torch.Tensor:
-    """Depth2Normal (diff_sugar_rasterizer_temporal.py:25-54): central differences with zero padding on
-    a [B,3,H,W] position map, normal = -cross(d/dx, d/dy)."""
-    p = F.pad(xyz_map, (1, 1, 1, 1))
-    ddx = p[:, :, 1:-1, 2:] - p[:, :, 1:-1, :-2]
-    ddy = p[:, :, 2:, 1:-1] - p[:, :, :-2, 1:-1]
-    return -torch.cross(ddx, ddy, dim=1)
-
-
-def _detach_outside(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-    """x[~mask] = x[~mask].detach() without boolean indexing (no host sync)."""
-    return torch.where(mask, x, x.detach())
 
 
 class DiffGaussianBatchRenderer:
@@ -45,6 +31,7 @@ class DiffGaussianBatchRenderer:
         self.capacity = capacity          # None: exact sizing with one num_rendered read-back per batch
         self.last_state = None
         self.last_view_params = None
+        self._bg_cache = None
 
     def batch_forward(self, batch: Dict[str, Any], compute_normal_from_dist: bool = True, node_attrs=None) -> Dict[str, Any]:
         geo = self.geometry
@@ -54,11 +41,15 @@ class DiffGaussianBatchRenderer:
         H, W = int(batch["height"]), int(batch["width"])
         fovy = batch["fovy"]
         # gaussian_batch_renderer.py:23-26 — fovx := fovy, znear .1, zfar 100
-        view, proj, campos, tanx, tany = get_cam_info_gaussian(c2w, fovy, fovy, znear=0.1, zfar=100.0)
-        bg = torch.tensor(self.back_ground_color, dtype=torch.float32, device=dev)
-        if not self.training:
-            bg = 1.0 - bg                                                       # temporal.py:96-103
-        bg6 = torch.cat([bg, bg]).expand(B, 6)                                  # the normal pass uses the same bg
+        # "cam_info" lets a caller that replays this method from a CUDA graph hand in the camera block it computed
+        # eagerly for the step (trainstep.GraphedDynamicStageStep); otherwise it is derived here
+        view, proj, campos, tanx, tany = batch["cam_info"] if "cam_info" in batch else \
+            get_cam_info_gaussian(c2w, fovy, fovy, znear=0.1, zfar=100.0)
+        bgc = self.back_ground_color if self.training else tuple(1.0 - c for c in self.back_ground_color)   # temporal.py:96-103
+        key = (bgc, str(dev))
+        if self._bg_cache is None or self._bg_cache[0] != key:      # built once: no pageable H2D copy per step
+            self._bg_cache = (key, torch.tensor(bgc + bgc, dtype=torch.float32, device=dev))
+        bg6 = self._bg_cache[1].expand(B, 6)                                    # the normal pass uses the same bg
 
         static = "timestamp" not in batch       # static stage: diff_sugar_rasterizer_normal.py:79-226
         P = geo.n_gaussians
@@ -83,28 +74,14 @@ class DiffGaussianBatchRenderer:
                 state_out=states)
         self.last_state = states[0]
         self.last_view_params = vp        # [B,48] camera block actually rasterized (include/dm4d.h layout)
-        rgb, nrm = color6[:, :3], color6[:, 3:]
-
-        mask = alpha > 0.99                                                     # temporal.py:180
-        depth = _detach_outside(depth, mask)                                    # :181
-        mask3 = mask.expand(-1, 3, -1, -1)
-        out = {}
-        if compute_normal_from_dist:
-            rays_o = batch["rays_o"].permute(0, 3, 1, 2)
-            rays_d = batch["rays_d"].permute(0, 3, 1, 2)
-            xyz_map = rays_o + depth * rays_d                                   # :187
-            nfd = F.normalize(depth_to_normal(xyz_map), dim=1)                  # :188-189
-            nfd_map = nfd * 0.5 * alpha + 0.5                                   # :190
-            out["comp_normal_from_dist"] = _detach_outside(nfd_map, mask3).permute(0, 2, 3, 1)   # :191-193
-        normal = F.normalize(nrm, dim=1)                                        # :212
-        normal_map = normal * 0.5 * alpha + 0.5                                 # :214
+        # image post-ops (temporal.py:180-193,212-218,229 / normal.py:172-206) for the whole batch: one fused
+        # forward kernel, outputs already [B,H,W,C]; its backward feeds the rasterizer backward directly
+        nfd = compute_normal_from_dist and "rays_o" in batch
+        out = post_ops(color6, depth, alpha, batch["rays_o"] if nfd else None, batch["rays_d"] if nfd else None,
+                       static=static, compute_normal_from_dist=nfd)
         out.update({
-            "comp_rgb": rgb.clamp(0, 1).permute(0, 2, 3, 1),                    # :229, batch renderer :79
-            "comp_normal": _detach_outside(normal_map, mask3).permute(0, 2, 3, 1),
-            "comp_depth": depth.permute(0, 2, 3, 1),
-            "comp_mask": alpha.permute(0, 2, 3, 1),
             "viewspace_points": screenspace,                                    # [B,P,3]; .grad holds the 2-D mean gradients
-            "visibility_filter": [radii[b] > 0 for b in range(B)],
-            "radii": [radii[b] for b in range(B)],
+            "visibility_filter": list((radii > 0).unbind(0)),
+            "radii": list(radii.unbind(0)),
         })
         return out

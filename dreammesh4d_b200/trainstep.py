@@ -15,6 +15,7 @@ from typing import Callable, Dict, Optional, Sequence
 import torch
 import torch.distributed as dist
 
+from .camera import get_cam_info_gaussian
 from .geometry import DynamicSuGaRGeometry, activate_node_deltas
 from .renderer import DiffGaussianBatchRenderer
 
@@ -71,3 +72,51 @@ class DynamicStageStep:
             geo.update_step(0, step)                           # per-substep caches (dynamic_sugar.py:863-873)
         self.opt.step()
         return total
+
+
+class GraphedDynamicStageStep:
+    """``DynamicStageStep`` captured into ONE CUDA graph: deformation network, fused skinning, rasterizer, post-ops,
+    losses, the whole backward and the optimizer update of every substep replay as a single launch, so the ~600
+    kernel launches of a step cost no host time (eager: the step is host/launch-bound, ~3x slower than its kernels).
+
+    Requirements: ``renderer.capacity`` is an integer (no ``num_rendered`` read-back), the optimizer was built with
+    ``capturable=True``, ``loss_fn`` has no host synchronisation, and every step uses batches of the shapes of
+    ``example_batches``.  Per step the tensor entries of the batches (cameras, timestamps, rays, targets) are copied
+    into the graph's static inputs; the camera matrices are derived eagerly before the replay (a batched 4x4
+    inverse is a library call that must not be captured).  Single-process: with a process group the node-gradient
+    exchange stays outside graphs, use ``DynamicStageStep``."""
+
+    def __init__(self, step: DynamicStageStep, example_batches: Sequence[Dict], warmup: int = 3):
+        if step.ren.capacity is None:
+            raise ValueError("GraphedDynamicStageStep needs renderer.capacity (an integer) to be set")
+        if dist.is_initialized() and dist.get_world_size(step.group) > 1:
+            raise ValueError("GraphedDynamicStageStep is single-process; use DynamicStageStep with a process group")
+        self.step = step
+        self.static = [self._with_cam({k: (v.clone() if torch.is_tensor(v) else v) for k, v in b.items()})
+                       for b in example_batches]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):            # warm-up steps are real optimizer steps
+            for i in range(warmup):
+                step(self.static, i)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = step(self.static, warmup)
+
+    @staticmethod
+    def _with_cam(b: Dict) -> Dict:
+        b["cam_info"] = tuple(t.contiguous() for t in get_cam_info_gaussian(b["c2w"], b["fovy"], b["fovy"], znear=0.1, zfar=100.0))
+        return b
+
+    def __call__(self, batches: Sequence[Dict]) -> torch.Tensor:
+        for st, b in zip(self.static, batches):
+            for k, v in b.items():
+                if torch.is_tensor(v):
+                    st[k].copy_(v, non_blocking=True)
+            cam = get_cam_info_gaussian(st["c2w"], st["fovy"], st["fovy"], znear=0.1, zfar=100.0)
+            for dst, src in zip(st["cam_info"], cam):
+                dst.copy_(src)
+        self.graph.replay()
+        return self.loss

@@ -21,6 +21,10 @@
  *                     fuse_rotations (:877-889), get_timed_gs_normals (:357-364)
  *   dm4d_sugar_rest_frames <- SuGaRModel.quaternions / get_gs_normals
  *                     (custom/threestudio-dreammesh4d/geometry/sugar.py:490-526)
+ *   dm4d_hexplane_* <- interpolate_ms_features / HexPlaneField.forward
+ *                     (custom/threestudio-dreammesh4d/geometry/deformation.py:141-174,242-248)
+ *   dm4d_postops_* <- the image post-ops of DiffGaussian.forward
+ *                     (custom/threestudio-dreammesh4d/renderer/diff_sugar_rasterizer_temporal.py:180-239)
  */
 #ifndef DM4D_H
 #define DM4D_H
@@ -200,6 +204,58 @@ int dm4d_arap_energy(const float* rest_verts, const int32_t* row_ptr, const int3
 int dm4d_mesh_normal_consistency(const int32_t* pairs, int32_t n_pairs, int32_t n_t, int32_t V, const float* verts,
                                  float* loss, float* dL_dverts, void* stream);
 
+/* ---- fused per-view image post-ops --------------------------------------------------
+ * Replaces the element-wise / convolution / boolean-index tail of DiffGaussian.forward
+ * (custom/threestudio-dreammesh4d/renderer/diff_sugar_rasterizer_temporal.py:180-193,212-218,229; Depth2Normal
+ * :25-54; static twin diff_sugar_rasterizer_normal.py:172-206) and the stack/permute of
+ * GaussianBatchRenderer.batch_forward (renderer/gaussian_batch_renderer.py:78-122).
+ * Inputs are the rasterizer's planar outputs of a 6-channel pass (rgb + rendered normals) plus the batch's rays;
+ * outputs are [n_views,H,W,C] (channel-last), exactly the comp_* tensors of the renderer's return dict. */
+#define DM4D_POSTOPS_NORMAL_FROM_DIST 1   /* compute comp_normal_from_dist (needs rays_o / rays_d) */
+#define DM4D_POSTOPS_STATIC 2             /* static renderer: the depth is detached outside the mask AFTER the position
+                                             map was built, so the stencil gradient reaches unmasked pixels */
+typedef struct dm4d_postops_desc {
+    int32_t n_views, H, W, flags;
+    const float* color6;   /* [n_views,6,H,W] */
+    const float* depth;    /* [n_views,1,H,W] */
+    const float* alpha;    /* [n_views,1,H,W] */
+    const float* rays_o;   /* [n_views,H,W,3] or NULL */
+    const float* rays_d;   /* [n_views,H,W,3] or NULL */
+} dm4d_postops_desc;
+
+/* comp_rgb, comp_normal, comp_normal_from_dist (NULL iff the flag is clear): [n_views,H,W,3];
+ * comp_depth, comp_mask: [n_views,H,W,1]. */
+int dm4d_postops_forward(const dm4d_postops_desc* d, float* comp_rgb, float* comp_normal,
+                         float* comp_normal_from_dist, float* comp_depth, float* comp_mask, void* stream);
+/* g_*: gradients w.r.t. the five outputs (any may be NULL = zero).  scratch: [n_views,H,W,6] floats, required with
+ * DM4D_POSTOPS_NORMAL_FROM_DIST.  Outputs (overwritten): d_color6 [n_views,6,H,W], d_depth, d_alpha [n_views,1,H,W]
+ * — the dL_dcolor / dL_ddepth / dL_dalpha inputs of dm4d_raster_backward.  No atomics: bit-reproducible. */
+int dm4d_postops_backward(const dm4d_postops_desc* d, const float* g_rgb, const float* g_normal,
+                          const float* g_normal_from_dist, const float* g_depth, const float* g_mask,
+                          float* scratch, float* d_color6, float* d_depth, float* d_alpha, void* stream);
+
+/* ---- fused HexPlane multi-scale feature lookup ------------------------------------
+ * Replaces interpolate_ms_features (custom/threestudio-dreammesh4d/geometry/deformation.py:141-174; grid_sample_wrapper
+ * :84-111 = bilinear, padding_mode='border', align_corners=True) as called by HexPlaneField.forward (:242-248):
+ *   features[n, s*feat + c] = prod over the 6 planes (i,j) in combinations(range(4),2) of
+ *                             bilinear(planes[s][p][c], coords[n,i], coords[n,j])
+ * coords [n_points,4]: normalised (x,y,z,t) (after normalize_aabb, :80-81).  planes[s][p]: the reference's parameter
+ * tensor of scale s, plane p, layout [1,feat,res[s][j],res[s][i]] (checkpoint-compatible).  res[s] = (x,y,z,t) sizes. */
+#define DM4D_HEX_MAX_SCALES 8
+typedef struct dm4d_hexplane_desc {
+    int32_t n_points, n_scales, feat, reserved;
+    const float* coords;
+    const float* planes[DM4D_HEX_MAX_SCALES][6];
+    int32_t res[DM4D_HEX_MAX_SCALES][4];
+} dm4d_hexplane_desc;
+/* features [n_points, n_scales*feat] (overwritten). */
+int dm4d_hexplane_forward(const dm4d_hexplane_desc* d, float* features, void* stream);
+/* dL_dplanes_host: HOST array of n_scales*6 DEVICE pointers (index s*6+p; NULL = skip that plane) to dense gradient
+ * tensors of the planes' shapes, ZEROED by the caller; the kernel adds into the touched texels (RED.ADD.F32).
+ * Coordinates receive no gradient (the control nodes and the timestamps are not trainable in the reference). */
+int dm4d_hexplane_backward(const dm4d_hexplane_desc* d, const float* dL_dfeatures, float* const* dL_dplanes_host,
+                           void* stream);
+
 /* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel launch).
  * Kernel ids: see DM4D_K_* below.  dm4d_profile_collect synchronises the recorded events, ADDS the
  * elapsed milliseconds / launch counts since the last collect into ms[DM4D_K_COUNT] /
@@ -207,7 +263,8 @@ int dm4d_mesh_normal_consistency(const int32_t* pairs, int32_t n_pairs, int32_t 
 enum {
     DM4D_K_PREPROCESS = 0, DM4D_K_SCAN, DM4D_K_SCATTER, DM4D_K_SORT_PACK, DM4D_K_RENDER_FWD,
     DM4D_K_RENDER_BWD, DM4D_K_PREPROCESS_BWD, DM4D_K_SKIN_VERT_FWD, DM4D_K_SKIN_GAUSS_FWD,
-    DM4D_K_SKIN_GAUSS_BWD, DM4D_K_SKIN_VERT_BWD, DM4D_K_REST_FRAMES, DM4D_K_ARAP, DM4D_K_NORMAL_CONS, DM4D_K_COUNT
+    DM4D_K_SKIN_GAUSS_BWD, DM4D_K_SKIN_VERT_BWD, DM4D_K_REST_FRAMES, DM4D_K_ARAP, DM4D_K_NORMAL_CONS,
+    DM4D_K_POSTOPS_FWD, DM4D_K_POSTOPS_BWD, DM4D_K_HEXPLANE_FWD, DM4D_K_HEXPLANE_BWD, DM4D_K_COUNT
 };
 int dm4d_profile_enable(int on);
 int dm4d_profile_collect(double* ms_host, int64_t* launches_host);

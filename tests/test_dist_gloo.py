@@ -53,7 +53,7 @@ def _worker_nodegrad(rank, world, port, ret):
         from dreammesh4d_b200.geometry import activate_node_deltas
         from dreammesh4d_b200.trainstep import node_attribute_backward
         torch.manual_seed(0)
-        net = HexPlaneDeformation(base_res=(8, 8, 8, 5), multires=(1, 2))
+        net = HexPlaneDeformation(base_res=(8, 8, 8, 5), multires=(1, 2), fused=False)   # CPU (gloo) test: PyTorch lookup
         with torch.no_grad():
             for head in (net.deformation_net.pos_deform, net.deformation_net.rotations_deform,
                          net.deformation_net.scales_deform, net.deformation_net.opacity_deform):

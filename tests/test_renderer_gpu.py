@@ -13,7 +13,8 @@ from dreammesh4d_b200 import synthetic
 from dreammesh4d_b200.camera import get_cam_info_gaussian
 from dreammesh4d_b200.deformation import HexPlaneDeformation
 from dreammesh4d_b200.geometry import DynamicSuGaRGeometry, activate_node_deltas
-from dreammesh4d_b200.renderer import DiffGaussianBatchRenderer, depth_to_normal
+from dreammesh4d_b200.renderer import DiffGaussianBatchRenderer
+from oracle import postops_oracle as PO
 from oracle import skin_oracle as SO
 from oracle.raster_oracle import RasterOracle
 from tests import helpers as Hh
@@ -44,6 +45,7 @@ def test_batch_forward_matches_oracle_chain():
                         (net.deformation_net.scales_deform, 0.03), (net.deformation_net.opacity_deform, 0.5)):
             head.feature_out[1].weight.normal_(0, s)
     net_cpu = copy.deepcopy(net)
+    net_cpu.deformation_net.grid.fused = False      # the oracle chain evaluates A1 as the reference does (F.grid_sample, CPU)
     geo = DynamicSuGaRGeometry(scene, graph, net).to(DEV)
     ren = DiffGaussianBatchRenderer(geo)
     c2w, fovy = synthetic.random_orbit_cameras(B, seed=8)
@@ -85,7 +87,7 @@ def test_batch_forward_matches_oracle_chain():
     ok = torch.stack(oks)[:, None]
     mask = alpha > 0.99
     xyz = rays_o.permute(0, 3, 1, 2) + depth * rays_d.permute(0, 3, 1, 2)
-    nfd = F.normalize(depth_to_normal(xyz), dim=1) * 0.5 * alpha + 0.5
+    nfd = F.normalize(PO.depth2normal(xyz), dim=1) * 0.5 * alpha + 0.5
     nrm = F.normalize(color6[:, 3:], dim=1) * 0.5 * alpha + 0.5
     expect = {"comp_rgb": color6[:, :3].clamp(0, 1), "comp_depth": depth, "comp_mask": alpha, "comp_normal": nrm,
               "comp_normal_from_dist": nfd}
@@ -232,3 +234,51 @@ def test_dynamic_stage_step_matches_end_to_end_autograd():
             assert Hh.rel_linf(p.grad.cpu().numpy(), want[n].cpu().numpy()) <= 1e-4, n
             checked += 1
     assert checked >= 8
+
+
+def test_graphed_dynamic_stage_step_equals_eager_steps():
+    """GraphedDynamicStageStep (whole optimizer step as one CUDA graph, new inputs copied into its static buffers)
+    walks the parameters exactly like the eager DynamicStageStep."""
+    from dreammesh4d_b200.trainstep import DynamicStageStep, GraphedDynamicStageStep
+    torch.manual_seed(0)
+    B, H, W = 2, 64, 64
+    scene = synthetic.make_sugar_scene(600, g=3)
+    graph = synthetic.make_deform_graph(scene.verts, 16, 4)
+    net_a = HexPlaneDeformation(base_res=(16, 16, 16, 5), multires=(1, 2))
+    with torch.no_grad():
+        for head, s in ((net_a.deformation_net.pos_deform, 0.02), (net_a.deformation_net.rotations_deform, 0.1),
+                        (net_a.deformation_net.scales_deform, 0.03), (net_a.deformation_net.opacity_deform, 0.5)):
+            head.feature_out[1].weight.normal_(0, s)
+    net_b = copy.deepcopy(net_a)
+    loss_fn = lambda out, b: F.mse_loss(out["comp_rgb"], b["rgb"]) + F.mse_loss(out["comp_mask"], b["mask"]) + \
+        0.1 * F.mse_loss(out["comp_normal_from_dist"], out["comp_normal"].detach())
+
+    def make_batch(seed):
+        c2w, fovy = synthetic.random_orbit_cameras(B, seed=seed)
+        rays_o, rays_d = make_rays(c2w, fovy, H, W)
+        g = torch.Generator().manual_seed(seed)
+        return {"c2w": c2w.to(DEV), "fovy": fovy.to(DEV), "height": H, "width": W,
+                "timestamp": torch.rand(B, generator=g).to(DEV), "rays_o": rays_o.to(DEV), "rays_d": rays_d.to(DEV),
+                "rgb": torch.rand(B, H, W, 3, generator=g).to(DEV), "mask": torch.ones(B, H, W, 1, device=DEV)}
+
+    first = [make_batch(1), make_batch(2)]
+    later = [[make_batch(3), make_batch(4)], [make_batch(5), make_batch(6)]]
+    steppers = []
+    for net in (net_a, net_b):
+        geo = DynamicSuGaRGeometry(scene, graph, net).to(DEV)
+        ren = DiffGaussianBatchRenderer(geo, capacity=200_000)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-15, capturable=True)
+        steppers.append(DynamicStageStep(geo, ren, opt, loss_fn))
+    eager, graphed_src = steppers
+    for i in range(3):
+        eager(first, i)
+    losses_e = [eager(b, 3 + i) for i, b in enumerate(later)]
+    graphed = GraphedDynamicStageStep(graphed_src, first, warmup=3)      # 3 real warm-up steps on `first`, then capture
+    losses_g = [graphed(b).clone() for b in later]
+    torch.cuda.synchronize()
+    assert not graphed_src.ren.last_state.status()[1]
+    for le, lg in zip(losses_e, losses_g):
+        assert abs(float(le) - float(lg)) <= 1e-4 * abs(float(le))
+    for (n, pa), (_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        assert Hh.rel_linf(pb.detach().cpu().numpy(), pa.detach().cpu().numpy()) <= 1e-4, n
+    assert torch.isfinite(losses_g[-1])
