@@ -88,7 +88,7 @@ def train_step_ms(scene, graph, cams, dev, dist, steps: int):
             head.feature_out[1].weight.normal_(0, sdev)
     geo = DynamicSuGaRGeometry(scene, graph, net).to(dev)
     ren = DiffGaussianBatchRenderer(geo)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99), eps=1e-15, capturable=True)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99), eps=1e-15, capturable=True, fused=True)
     batches = []
     for (c2w, fovy) in cams:
         focal = 0.5 * H / torch.tan(0.5 * fovy)

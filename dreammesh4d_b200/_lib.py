@@ -85,6 +85,7 @@ SIGNATURES = {
     "dm4d_postops_backward": (ctypes.c_int, [POINTER(PostopsDesc)] + [c_void_p] * 10),
     "dm4d_hexplane_forward": (ctypes.c_int, [POINTER(HexplaneDesc), c_void_p, c_void_p]),
     "dm4d_hexplane_backward": (ctypes.c_int, [POINTER(HexplaneDesc), c_void_p, POINTER(c_void_p), c_void_p]),
+    "dm4d_graph_knn": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dm4d_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "dm4d_profile_collect": (ctypes.c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
     "dm4d_kernel_name": (c_char_p, [ctypes.c_int]),
@@ -92,7 +93,7 @@ SIGNATURES = {
     "dm4d_version": (ctypes.c_int, []),
 }
 
-K_COUNT = 18
+K_COUNT = 19
 
 _lib = None
 

@@ -28,6 +28,7 @@ UNITS = {
     "skin.cu": [],
     "postops.cu": [],
     "hexplane.cu": [],
+    "graph.cu": [],
     "capi.cu": [],
 }
 

@@ -53,12 +53,18 @@ constexpr int WSTAGES = DM4D_WSTAGES;   // per-warp ring depth
 constexpr int FWD_UNROLL = DM4D_FWD_UNROLL;
 static_assert(WCHUNK == 64, "the per-half-warp candidate queue is one 64-bit word per staged chunk");
 
-// exp of the (non-positive, >= -5.6 where it matters) Gaussian exponent: ex2.approx(x * log2 e), 2 instructions
-// instead of expf's 10; relative error < 5e-7, far inside the image tolerance and the parity tests' threshold-ambiguity
-// margin (2e-5).  Forward and backward use the same function, so their contribution decisions agree bit for bit.
+// exp of the Gaussian exponent.  expf (2 ulp) by default: DM4D_FAST_EXP switches to ex2.approx(x * log2 e), 6
+// instructions shorter (-4 % step time) but 2 + |1.17 x| ulp; at C4 (about 100 blended Gaussians per pixel) the
+// cancellation in (colour - accumulated colour) amplifies that to ~1e-3 of the largest gradient, the edge of the parity
+// tolerance (scripts/c4_errors.py), so it stays opt-in.  Forward and backward use the same function, so their
+// contribution decisions agree bit for bit either way.
+#ifdef DM4D_FAST_EXP
 __device__ __forceinline__ float gauss_exp(float x) { return __expf(x); }
+#else
+__device__ __forceinline__ float gauss_exp(float x) { return expf(x); }
+#endif
 __device__ __forceinline__ float fast_rcp(float x) {
-    float r;
+    float r;      // MUFU.RCP, 1 ulp: no measurable effect on the gradient error (scripts/c4_errors.py)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }

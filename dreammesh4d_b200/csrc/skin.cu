@@ -692,9 +692,13 @@ extern "C" int dm4d_arap_energy(const float* rest_verts, const int32_t* row_ptr,
 namespace {
 __global__ void __launch_bounds__(DM4D_BLOCK) normal_consistency_kernel(const int32_t* pairs, int n_pairs, int n_t, int V,
                                                                         const float* verts, float* loss, float* dverts) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)n_t * n_pairs) return;
-    const int t = (int)(idx / n_pairs), p = (int)(idx - (long long)t * n_pairs);
+    // grid = (pair blocks, timestamps): a block belongs to ONE timestamp, so its loss terms are reduced in the
+    // block and leave as one atomic (150k same-address atomics per timestamp serialised the old kernel: 1.85 ms)
+    __shared__ float warp_part[DM4D_BLOCK / 32];
+    const int t = blockIdx.y, p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = p < n_pairs;
+    float term = 0.f;
+    if (live) {
     const int i0 = pairs[p * 4], i1 = pairs[p * 4 + 1], ia = pairs[p * 4 + 2], ib = pairs[p * 4 + 3];
     const size_t vb = (size_t)t * V;
     const f3 v0 = ld3(verts + (vb + i0) * 3), v1 = ld3(verts + (vb + i1) * 3), a = ld3(verts + (vb + ia) * 3),
@@ -707,8 +711,8 @@ __global__ void __launch_bounds__(DM4D_BLOCK) normal_consistency_kernel(const in
     const float c0 = fmaxf(l0, 1e-8f), c1 = fmaxf(l1, 1e-8f);
     const float cosv = dot(n0, m1) / (c0 * c1);
     const float wgt = 1.0f / (float)n_pairs;
-    atomicAdd(loss + t, (1.0f - cosv) * wgt);
-    if (!dverts) return;
+    term = (1.0f - cosv) * wgt;
+    if (dverts) {
     // d(-cos)/dn0 = -(m1/(c0 c1) - cos * n0 / c0^2)   (norm clamp treated as inactive when l > eps)
     const f3 g0 = (-wgt) * ((1.f / (c0 * c1)) * m1 - ((l0 > 1e-8f ? cosv / (c0 * c0) : 0.f)) * n0);
     const f3 g1 = (-wgt) * ((1.f / (c0 * c1)) * n0 - ((l1 > 1e-8f ? cosv / (c1 * c1) : 0.f)) * m1);   // w.r.t. m1 = -n1
@@ -723,6 +727,18 @@ __global__ void __launch_bounds__(DM4D_BLOCK) normal_consistency_kernel(const in
     atomicAdd(q1, de.x); atomicAdd(q1 + 1, de.y); atomicAdd(q1 + 2, de.z);
     atomicAdd(qa, dea.x); atomicAdd(qa + 1, dea.y); atomicAdd(qa + 2, dea.z);
     atomicAdd(qb, deb.x); atomicAdd(qb + 1, deb.y); atomicAdd(qb + 2, deb.z);
+    }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = term;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < DM4D_BLOCK / 32; ++w) tot += warp_part[w];
+        atomicAdd(loss + t, tot);
+    }
 }
 }  // namespace
 
@@ -735,8 +751,9 @@ extern "C" int dm4d_mesh_normal_consistency(const int32_t* pairs, int32_t n_pair
     cudaStream_t s = (cudaStream_t)stream;
     DM4D_CUDA_CHECK(cudaMemsetAsync(loss, 0, (size_t)n_t * sizeof(float), s));
     if (dL_dverts) DM4D_CUDA_CHECK(cudaMemsetAsync(dL_dverts, 0, (size_t)n_t * V * 3 * sizeof(float), s));
-    const long long n = (long long)n_t * n_pairs;
-    { KernelTimer kt(DM4D_K_NORMAL_CONS, s); normal_consistency_kernel<<<(unsigned)((n + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(pairs, n_pairs, n_t, V, verts, loss, dL_dverts); }
+    if (n_t > 65535) { dm4d_set_error("dm4d_mesh_normal_consistency: n_t > 65535"); return DM4D_EINVAL; }
+    const dim3 grid((unsigned)((n_pairs + DM4D_BLOCK - 1) / DM4D_BLOCK), (unsigned)n_t);
+    { KernelTimer kt(DM4D_K_NORMAL_CONS, s); normal_consistency_kernel<<<grid, DM4D_BLOCK, 0, s>>>(pairs, n_pairs, n_t, V, verts, loss, dL_dverts); }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }

@@ -21,6 +21,8 @@
  *                     fuse_rotations (:877-889), get_timed_gs_normals (:357-364)
  *   dm4d_sugar_rest_frames <- SuGaRModel.quaternions / get_gs_normals
  *                     (custom/threestudio-dreammesh4d/geometry/sugar.py:490-526)
+ *   dm4d_graph_knn <- DynamicSuGaRModel.build_deformation_graph, mode "eucdisc"
+ *                     (custom/threestudio-dreammesh4d/geometry/dynamic_sugar.py:745-790,853-861)
  *   dm4d_hexplane_* <- interpolate_ms_features / HexPlaneField.forward
  *                     (custom/threestudio-dreammesh4d/geometry/deformation.py:141-174,242-248)
  *   dm4d_postops_* <- the image post-ops of DiffGaussian.forward
@@ -256,6 +258,15 @@ int dm4d_hexplane_forward(const dm4d_hexplane_desc* d, float* features, void* st
 int dm4d_hexplane_backward(const dm4d_hexplane_desc* d, const float* dL_dfeatures, float* const* dL_dplanes_host,
                            void* stream);
 
+/* ---- deformation-graph construction ---------------------------------------------------
+ * K nearest `nodes` [n_nodes,3] of every query point [n_queries,3], Euclidean: replaces the per-vertex Open3D KD-tree
+ * queries of DynamicSuGaRModel.build_deformation_graph, mode "eucdisc"
+ * (custom/threestudio-dreammesh4d/geometry/dynamic_sugar.py:765-790).  Outputs (overwritten): idx [n_queries,k] node
+ * indices ordered by ascending (squared distance, index), sqdist [n_queries,k] (may be NULL) the SQUARED distances —
+ * exactly the [1] and [2] results of KDTreeFlann.search_knn_vector_3d.  1 <= k <= min(17, n_nodes). */
+int dm4d_graph_knn(const float* queries, int32_t n_queries, const float* nodes, int32_t n_nodes, int32_t k,
+                   int32_t* idx, float* sqdist, void* stream);
+
 /* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel launch).
  * Kernel ids: see DM4D_K_* below.  dm4d_profile_collect synchronises the recorded events, ADDS the
  * elapsed milliseconds / launch counts since the last collect into ms[DM4D_K_COUNT] /
@@ -264,7 +275,8 @@ enum {
     DM4D_K_PREPROCESS = 0, DM4D_K_SCAN, DM4D_K_SCATTER, DM4D_K_SORT_PACK, DM4D_K_RENDER_FWD,
     DM4D_K_RENDER_BWD, DM4D_K_PREPROCESS_BWD, DM4D_K_SKIN_VERT_FWD, DM4D_K_SKIN_GAUSS_FWD,
     DM4D_K_SKIN_GAUSS_BWD, DM4D_K_SKIN_VERT_BWD, DM4D_K_REST_FRAMES, DM4D_K_ARAP, DM4D_K_NORMAL_CONS,
-    DM4D_K_POSTOPS_FWD, DM4D_K_POSTOPS_BWD, DM4D_K_HEXPLANE_FWD, DM4D_K_HEXPLANE_BWD, DM4D_K_COUNT
+    DM4D_K_POSTOPS_FWD, DM4D_K_POSTOPS_BWD, DM4D_K_HEXPLANE_FWD, DM4D_K_HEXPLANE_BWD,
+    DM4D_K_GRAPH_KNN, DM4D_K_COUNT
 };
 int dm4d_profile_enable(int on);
 int dm4d_profile_collect(double* ms_host, int64_t* launches_host);

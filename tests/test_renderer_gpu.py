@@ -263,22 +263,32 @@ def test_graphed_dynamic_stage_step_equals_eager_steps():
 
     first = [make_batch(1), make_batch(2)]
     later = [[make_batch(3), make_batch(4)], [make_batch(5), make_batch(6)]]
+    init = {n: p.detach().clone().to(DEV) for n, p in net_a.named_parameters()}
     steppers = []
     for net in (net_a, net_b):
         geo = DynamicSuGaRGeometry(scene, graph, net).to(DEV)
         ren = DiffGaussianBatchRenderer(geo, capacity=200_000)
-        opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-15, capturable=True)
+        # plain SGD: linear in the gradients, so the summation-order noise of the atomics stays small
+        # (Adam's m / sqrt(v) turns a sign flip of a near-zero gradient into a full lr-sized step)
+        opt = torch.optim.SGD(net.parameters(), lr=1e-3)
         steppers.append(DynamicStageStep(geo, ren, opt, loss_fn))
     eager, graphed_src = steppers
-    for i in range(3):
-        eager(first, i)
-    losses_e = [eager(b, 3 + i) for i, b in enumerate(later)]
-    graphed = GraphedDynamicStageStep(graphed_src, first, warmup=3)      # 3 real warm-up steps on `first`, then capture
+    eager(first, 0)
+    losses_e = [eager(b, 1 + i) for i, b in enumerate(later)]
+    graphed = GraphedDynamicStageStep(graphed_src, first, warmup=1)      # 1 real warm-up step on `first`, then capture
     losses_g = [graphed(b).clone() for b in later]
     torch.cuda.synchronize()
     assert not graphed_src.ren.last_state.status()[1]
     for le, lg in zip(losses_e, losses_g):
         assert abs(float(le) - float(lg)) <= 1e-4 * abs(float(le))
+    # the parameter UPDATES of the three steps agree (a stale graph input or a substep left out of the capture
+    # would change them at the 100 % level; run-to-run atomics noise through the hard mask thresholds is ~1e-4)
+    moved = 0
     for (n, pa), (_, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
-        assert Hh.rel_linf(pb.detach().cpu().numpy(), pa.detach().cpu().numpy()) <= 1e-4, n
-    assert torch.isfinite(losses_g[-1])
+        da, db = (pa.detach() - init[n]).cpu().numpy(), (pb.detach() - init[n]).cpu().numpy()
+        if np.abs(da).max() == 0:
+            assert np.abs(db).max() == 0, n
+            continue
+        assert Hh.rel_linf(db, da) <= 5e-3, n
+        moved += 1
+    assert moved >= 8 and torch.isfinite(losses_g[-1])
