@@ -267,71 +267,101 @@ __device__ void smem_merge_sort(unsigned long long* sk, int n) {
 
 // Copies one projected record into the sorted stream, replacing the contribution threshold by the tile-local
 // 16-bit CELL MASK: bit (4 cy + cx) set <=> some pixel of the 4x4 cell (cx, cy) of the tile can reach
-// alpha >= 1/255.  Exact ellipse-vs-rectangle test: the minimum of q(x,y) = cx x^2 + 2 cy x y + cz y^2 (positive
-// definite) over the cell's rectangle is 0 if it contains the centre, else it lies on one of the four edges,
-// where q is a 1-D parabola whose minimiser is clamped to the edge.  Conservative by the margins; never drops a
-// contributing pixel.  The render kernels walk, per half-warp, only the instances whose bit for its cell is set.
-__device__ __forceinline__ void pack_record(const float4* __restrict__ src, float4* __restrict__ dst, int r4,
-                                            float tile_x0, float tile_y0) {
-    const float4 a = src[0];
-    float4 b = src[1];
+// alpha >= 1/255, i.e. the cell's rectangle meets the ellipse E = {q(x,y) = cx x^2 + 2 cy x y + cz y^2 <= thr}.
+// Exact test, one cell ROW at a time: E cut by the row's horizontal strip y0 <= y <= y1 is convex, so it meets a
+// cell [x0,x1] x [y0,y1] iff its projection [xl, xr] on the x axis overlaps [x0, x1].  xr is the ellipse's
+// rightmost point +X if that point lies inside the strip, else the larger right end of the two chords cut by the
+// strip's edges (clamped to the ellipse's own y range); xl likewise.  About 160 instructions per instance instead of
+// the 1300 of testing the four edges of all 16 rectangles.  Conservative by the 0.01 px margins (the arithmetic error
+// is below 1e-4 px); never drops a contributing pixel.  The render kernels walk, per half-warp, only the instances
+// whose bit for its cell is set.
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ unsigned int cell_mask(const float4 a, const float4 b, float tile_x0, float tile_y0) {
     const float thr = b.z;
     unsigned int mask = 0u;
     if (thr > 0.f) {
         const float cx = a.z, cy = a.w, cz = b.x;
-        if (!(cx > 0.f) || !(cz > 0.f) || !(cx * cz - cy * cy > 0.f) || !(thr < 1e29f)) {
+        const float det = cx * cz - cy * cy;
+        if (!(cx > 0.f) || !(cz > 0.f) || !(det > 0.f) || !(thr < 1e29f)) {
             mask = 0xffffu;
         } else {
-            const float icx = 1.f / cx, icz = 1.f / cz, cy2 = 2.f * cy;
-            // vertical edges of the four cell columns: x = x0[i], x1[i] (pixel - centre, with margin)
-            float x0[4], x1[4], ys0[4], ys1[4], qx0[4], qx1[4];
-            bool xin[4];
+            const float icx = 1.f / cx, idet = 1.f / det;
+            const float X = sqrt_approx(thr * cz * idet), Y = sqrt_approx(thr * cx * idet);   // half extents of E
+            const float yX = -cy * X / cz;                 // y of the rightmost point (+X, yX); leftmost is (-X, -yX)
+            const float tcx = thr * cx;
+            float x0[4];                                   // left edges of the cell columns (pixel - centre, with margin)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                x0[i] = tile_x0 + (float)(4 * i) - a.x - 0.01f;
-                x1[i] = x0[i] + 3.02f;
-                ys0[i] = -cy * x0[i] * icz;            // unconstrained minimisers along the edges
-                ys1[i] = -cy * x1[i] * icz;
-                qx0[i] = cx * x0[i] * x0[i];
-                qx1[i] = cx * x1[i] * x1[i];
-                xin[i] = x0[i] <= 0.f && 0.f <= x1[i];
-            }
+            for (int i = 0; i < 4; ++i) x0[i] = tile_x0 + (float)(4 * i) - a.x - 0.01f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float y0 = tile_y0 + (float)(4 * j) - a.y - 0.01f, y1 = y0 + 3.02f;
-                const float xs0 = -cy * y0 * icx, xs1 = -cy * y1 * icx;
-                const float qy0 = cz * y0 * y0, qy1 = cz * y1 * y1;
-                const bool yin = y0 <= 0.f && 0.f <= y1;
+                if (y0 > Y || y1 < -Y) continue;                                   // the strip misses E
+                const float ya = fminf(fmaxf(y0, -Y), Y), yb = fminf(fmaxf(y1, -Y), Y);
+                const float da = sqrt_approx(fmaxf(tcx - det * ya * ya, 0.f)), db = sqrt_approx(fmaxf(tcx - det * yb * yb, 0.f));
+                float xr = fmaxf((da - cy * ya) * icx, (db - cy * yb) * icx);
+                float xl = fminf((-da - cy * ya) * icx, (-db - cy * yb) * icx);
+                if (yX >= y0 && yX <= y1) xr = X;
+                if (-yX >= y0 && -yX <= y1) xl = -X;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float qmin = 0.f;
-                    if (!(xin[i] && yin)) {
-                        const float ya = fminf(fmaxf(ys0[i], y0), y1), yb = fminf(fmaxf(ys1[i], y0), y1);
-                        const float xa = fminf(fmaxf(xs0, x0[i]), x1[i]), xb = fminf(fmaxf(xs1, x0[i]), x1[i]);
-                        const float qa = qx0[i] + (cy2 * x0[i] + cz * ya) * ya;      // on x = x0
-                        const float qb = qx1[i] + (cy2 * x1[i] + cz * yb) * yb;      // on x = x1
-                        const float qc = qy0 + (cy2 * y0 + cx * xa) * xa;            // on y = y0
-                        const float qd = qy1 + (cy2 * y1 + cx * xb) * xb;            // on y = y1
-                        qmin = fminf(fminf(qa, qb), fminf(qc, qd));
-                    }
-                    if (qmin <= thr) mask |= 1u << (4 * j + i);
-                }
+                for (int i = 0; i < 4; ++i)
+                    if (xl <= x0[i] + 3.02f && xr >= x0[i]) mask |= 1u << (4 * j + i);
             }
         }
     }
-    b.z = __uint_as_float(mask);
-    dst[0] = a;
-    dst[1] = b;
-    for (int q = 2; q < r4; ++q) dst[q] = src[q];
+    return mask;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) sort_pack_kernel(RasterLayout L) {
-    extern __shared__ __align__(16) unsigned long long sk[];   // [SORT_CHUNK]
+// Gathers the records of sorted instances [0, n) of a tile (ids in `keys`) into the packed stream.  Two instances per
+// thread and iteration with DM4D_PACK_UNROLL=2 (both gathers in flight before either mask is computed); measured
+// no better than 1 (the extra staging registers cost as much occupancy as the overlap gains), so 1 is the default.
+#ifndef DM4D_PACK_UNROLL
+#define DM4D_PACK_UNROLL 1
+#endif
+template <int R4>
+__device__ __forceinline__ void pack_tile(const unsigned long long* keys, int n, const float4* __restrict__ grec,
+                                          float4* __restrict__ srec, float tile_x0, float tile_y0) {
+    constexpr int U = DM4D_PACK_UNROLL;
+    for (int i0 = threadIdx.x; i0 < n; i0 += U * blockDim.x) {
+        float4 r[U][R4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = min(i0 + u * (int)blockDim.x, n - 1);
+            const float4* src = grec + (size_t)(unsigned int)(keys[i] & 0xffffffffull) * R4;
+#pragma unroll
+            for (int q = 0; q < R4; ++q) r[u][q] = src[q];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * (int)blockDim.x;
+            if (i < n) {
+                r[u][1].z = __uint_as_float(cell_mask(r[u][0], r[u][1], tile_x0, tile_y0));
+                float4* dst = srec + (size_t)i * R4;
+#pragma unroll
+                for (int q = 0; q < R4; ++q) dst[q] = r[u][q];
+            }
+        }
+    }
+}
+
+// Two CTA sizes share the tiles by segment length: 128 threads up to 1024 keys, 512 above (at C3 a tile holds ~1100
+// instances: a 512-thread CTA runs its merge passes with a quarter of its threads while the others wait at the pass
+// barriers; small CTAs keep more tiles resident per SM and their barriers span 4 warps).  Measured at C3: one size
+// 0.365 ms, two sizes 0.319 ms, three sizes (128/256/512) 0.372 ms — every extra launch adds its own tail.
+template <int THREADS, int CHUNK, int R4>
+__global__ void __launch_bounds__(THREADS) sort_pack_kernel(RasterLayout L, int n_lo, int n_hi) {
+    constexpr int SORT_CHUNK = CHUNK;
+    constexpr int SORT_THREADS = THREADS;
+    extern __shared__ __align__(16) unsigned long long sk[];   // [CHUNK]
     if (L.hdr->overflow) return;
     const int tile = (int)L.tile_order[blockIdx.x];   // global (view, tile) index, heaviest first
     const unsigned int beg = L.tile_offset[tile];
     const int n = (int)(L.tile_offset[tile + 1] - beg);
-    if (n == 0) return;
+    if (n <= n_lo || n > n_hi) return;
     const int v = tile / L.tiles;
     unsigned long long* gk = L.keys + beg;
     int npow2 = 2;
@@ -339,7 +369,6 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pack_kernel(RasterLayout L)
 
     const float4* grec = reinterpret_cast<const float4*>(L.g_rec + (size_t)v * L.P * L.rec);
     float4* srec = reinterpret_cast<float4*>(L.stream + (size_t)beg * L.rec);
-    const int r4 = L.rec / 4;
     const float tile_y0 = (float)(((tile - v * L.tiles) / L.gx) * DM4D_TILE);
     const float tile_x0 = (float)(((tile - v * L.tiles) % L.gx) * DM4D_TILE);
 
@@ -349,10 +378,8 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pack_kernel(RasterLayout L)
         __syncthreads();
         if (MS_E * SORT_THREADS >= SORT_CHUNK) smem_merge_sort(sk, n);
         else smem_network(sk, npow2, 2, npow2);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const unsigned int id = (unsigned int)(sk[i] & 0xffffffffull);
-            pack_record(grec + (size_t)id * r4, srec + (size_t)i * r4, r4, tile_x0, tile_y0);
-        }
+        __syncthreads();
+        pack_tile<R4>(sk, n, grec, srec, tile_x0, tile_y0);
         return;
     }
 
@@ -396,10 +423,8 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_pack_kernel(RasterLayout L)
             __syncthreads();
         }
     }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned int id = (unsigned int)(gk[i] & 0xffffffffull);
-        pack_record(grec + (size_t)id * r4, srec + (size_t)i * r4, r4, tile_x0, tile_y0);
-    }
+    __syncthreads();
+    pack_tile<R4>(gk, n, grec, srec, tile_x0, tile_y0);
 }
 
 __global__ void export_state_kernel(RasterLayout L, int view, unsigned int* ranges, unsigned int* point_list,
@@ -420,6 +445,20 @@ __global__ void export_state_kernel(RasterLayout L, int view, unsigned int* rang
 
 }  // namespace
 
+template <int R4>
+int launch_sort_pack_t(const RasterLayout& L, cudaStream_t s) {
+    static bool configured = false;
+    const size_t smem = (size_t)SORT_CHUNK * sizeof(unsigned long long);
+    if (!configured) {
+        DM4D_CUDA_CHECK(cudaFuncSetAttribute(sort_pack_kernel<SORT_THREADS, SORT_CHUNK, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const unsigned grid = (unsigned)(L.n_views * L.tiles);
+    sort_pack_kernel<SORT_THREADS, SORT_CHUNK, R4><<<grid, SORT_THREADS, smem, s>>>(L, 1024, 0x7fffffff);
+    sort_pack_kernel<128, 1024, R4><<<grid, 128, 1024 * sizeof(unsigned long long), s>>>(L, 0, 1024);
+    return DM4D_OK;
+}
+
 int launch_scan(const RasterLayout& L, cudaStream_t s) {
     { KernelTimer kt(DM4D_K_SCAN, s); scan_tiles_kernel<<<1, SCAN_THREADS, 0, s>>>(L); }
     DM4D_CUDA_CHECK(cudaGetLastError());
@@ -432,14 +471,9 @@ int launch_scatter_sort_pack(const RasterLayout& L, cudaStream_t s) {
     { KernelTimer kt(DM4D_K_SCATTER, s); scatter_kernel<<<(unsigned)((n + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(L); }
     DM4D_CUDA_CHECK(cudaGetLastError());
     {
-        static bool configured = false;
-        const size_t smem = (size_t)SORT_CHUNK * sizeof(unsigned long long);
-        if (!configured) {
-            DM4D_CUDA_CHECK(cudaFuncSetAttribute(sort_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
         KernelTimer kt(DM4D_K_SORT_PACK, s);
-        sort_pack_kernel<<<(unsigned)(L.n_views * L.tiles), SORT_THREADS, smem, s>>>(L);
+        const int rc = L.rec == 12 ? launch_sort_pack_t<3>(L, s) : launch_sort_pack_t<4>(L, s);
+        if (rc) return rc;
     }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
