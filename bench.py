@@ -493,7 +493,7 @@ def run_ours(args):
             ref_eq = ref_equiv_ms(dev_in, vp, gC, gD, gA, P, steps=max(3, min(args.steps, 10)))
             log(f"ref-equivalent pipeline: {ref_eq['ms_per_step']:.3f} ms/step")
             # the reference renders RGB and normals as TWO rasterizer calls per view (temporal.py:169-178, 202-211); the
-            # product fuses them into one 6-channel pass: time that pass on the same views (eager launches, CUDA events)
+            # product fuses them into one 6-channel pass: time that pass on the same views, like `value`
             nrm = gs["normals"].to(dev).contiguous().requires_grad_(True)
             g6 = torch.cat([gC, gC.flip(1)], dim=1).contiguous()
             vp6 = R.make_view_params(d(V), d(PV), d(campos), tanx, tany, torch.ones(VIEWS, 6, device=dev), set_index=set_idx)
@@ -504,16 +504,8 @@ def run_ours(args):
                 torch.autograd.backward([c6, dep, alp], [g6, gD, gA])
                 for t_ in list(dev_in.values()) + [nrm]:
                     t_.grad = None
-            for _ in range(3):
-                six()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(10):
-                six()
-            e1.record()
-            torch.cuda.synchronize()
-            six_ms = e0.elapsed_time(e1) / 10
+            replay6, _ = make_runner(six)           # same launch mode as `value`: one CUDA-graph replay per step
+            six_ms = timed(replay6, 10) / 10
             ref_eq["rgb_plus_normal"] = {"ours_fused_6ch_ms": six_ms, "ref_equiv_two_passes_ms": 2 * ref_eq["ms_per_step"],
                                          "speedup": round(2 * ref_eq["ms_per_step"] / six_ms, 2),
                                          "what": "what the reference's renderer asks of the rasterizer per step: RGB and normal "

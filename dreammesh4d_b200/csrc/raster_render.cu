@@ -51,7 +51,7 @@ constexpr int WSTAGES = DM4D_WSTAGES;   // per-warp ring depth
 #define DM4D_FWD_UNROLL 4
 #endif
 constexpr int FWD_UNROLL = DM4D_FWD_UNROLL;
-static_assert(WCHUNK == 64, "the per-half-warp candidate queue is one 64-bit word per staged chunk");
+static_assert(WCHUNK == 64, "the per-half-warp candidate queue covers one staged chunk of 64 instances");
 
 // exp of the Gaussian exponent.  expf (2 ulp) by default: DM4D_FAST_EXP switches to ex2.approx(x * log2 e), 6
 // instructions shorter (-4 % step time) but 2 + |1.17 x| ulp; at C4 (about 100 blended Gaussians per pixel) the
@@ -82,16 +82,44 @@ struct PixelMap {
     }
 };
 
-// Candidate queue of this lane's half-warp for one staged chunk: bit j set <=> instance j of the chunk can reach
-// the half-warp's cell.  Four warp ballots (two cells x two 32-instance groups); uniform within a half-warp.
+// Candidate queue of this lane's half-warp for one staged chunk of 64 instances: bit j set <=> instance j of the chunk
+// can reach the half-warp's cell.  Four warp ballots (two cells x two 32-instance groups); uniform within a half-warp.
+// Kept as two 32-bit words: a pop is FLO + shift + mask on one word instead of 64-bit arithmetic.
+struct CellQueue {
+    unsigned int lo, hi;
+    __device__ __forceinline__ bool empty() const { return (lo | hi) == 0u; }
+    __device__ __forceinline__ void clear() { lo = hi = 0u; }
+    // front to back (forward): lowest set bit, or -1
+    __device__ __forceinline__ int pop_front() {
+        const bool in_lo = lo != 0u;
+        unsigned int cur = in_lo ? lo : hi;
+        const int j = cur ? (__ffs((int)cur) - 1 + (in_lo ? 0 : 32)) : -1;
+        cur &= cur - 1u;
+        if (in_lo) lo = cur; else hi = cur;
+        return j;
+    }
+    // back to front (backward): highest set bit; the queue must not be empty
+    __device__ __forceinline__ int pop_back() {
+        const bool in_hi = hi != 0u;
+        unsigned int cur = in_hi ? hi : lo;
+        const int b = 31 - __clz((int)cur);
+        cur &= ~(1u << b);
+        if (in_hi) hi = cur; else lo = cur;
+        return b + (in_hi ? 32 : 0);
+    }
+};
+
 template <int R4>
-__device__ __forceinline__ unsigned long long cell_queue(const float4* r, int cnt, int lane, int warp, int half) {
+__device__ __forceinline__ CellQueue cell_queue(const float4* r, int cnt, int lane, int warp, int half) {
     const unsigned int m0 = lane < cnt ? __float_as_uint(r[lane * R4 + 1].z) : 0u;
     const unsigned int m1 = lane + 32 < cnt ? __float_as_uint(r[(lane + 32) * R4 + 1].z) : 0u;
     const int sh = 2 * warp;
     const unsigned int a0 = __ballot_sync(0xffffffffu, (m0 >> sh) & 1u), b0 = __ballot_sync(0xffffffffu, (m0 >> (sh + 1)) & 1u);
     const unsigned int a1 = __ballot_sync(0xffffffffu, (m1 >> sh) & 1u), b1 = __ballot_sync(0xffffffffu, (m1 >> (sh + 1)) & 1u);
-    return half ? (((unsigned long long)b1 << 32) | b0) : (((unsigned long long)a1 << 32) | a0);
+    CellQueue q;
+    q.lo = half ? b0 : a0;
+    q.hi = half ? b1 : a1;
+    return q;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -224,18 +252,15 @@ __global__ void __launch_bounds__(THREADS) render_forward_kernel(RasterLayout L,
             const int slot = c % WSTAGES;
             const float4* r = ring.wait(slot, c / WSTAGES);
             const int cnt = min(WCHUNK, n - c * WCHUNK);
-            unsigned long long q = cell_queue<TR::R4>(r, cnt, lane, warp, pm.half);
-            if (done) q = 0ull;
-            while (__any_sync(0xffffffffu, q != 0ull)) {
+            CellQueue q = cell_queue<TR::R4>(r, cnt, lane, warp, pm.half);
+            if (done) q.clear();
+            while (__any_sync(0xffffffffu, !q.empty())) {
                 // Take up to FWD_UNROLL candidates of this half-warp's queue at once: their loads, power and exp
                 // are independent, only the blend below is sequential.
                 int js[FWD_UNROLL];
                 float al[FWD_UNROLL];
 #pragma unroll
-                for (int u = 0; u < FWD_UNROLL; ++u) {
-                    js[u] = q ? __ffsll((long long)q) - 1 : -1;
-                    q &= q - 1ull;
-                }
+                for (int u = 0; u < FWD_UNROLL; ++u) js[u] = q.pop_front();
 #pragma unroll
                 for (int u = 0; u < FWD_UNROLL; ++u) {
                     al[u] = 0.f;
@@ -266,7 +291,7 @@ __global__ void __launch_bounds__(THREADS) render_forward_kernel(RasterLayout L,
                         last = (unsigned int)(c * WCHUNK + js[u] + 1);
                     }
                 }
-                if (done) q = 0ull;
+                if (done) q.clear();
             }
             warp_done = __all_sync(0xffffffffu, done);
             __syncwarp();
@@ -421,12 +446,11 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
         const int sl = k % WSTAGES;
         const float4* r = ring.wait(sl, k / WSTAGES);
         const int cnt = min(WCHUNK, nlive - c * WCHUNK);
-        unsigned long long q = cell_queue<TR::R4>(r, cnt, lane, warp, pm.half);
-        while (__any_sync(0xffffffffu, q != 0ull)) {
+        CellQueue q = cell_queue<TR::R4>(r, cnt, lane, warp, pm.half);
+        while (__any_sync(0xffffffffu, !q.empty())) {
             // next instance of this half-warp's queue, back to front (the two halves walk different instances)
-            const bool have = q != 0ull;
-            const int j = have ? 63 - __clzll((long long)q) : 0;
-            q &= ~(1ull << j);
+            const bool have = !q.empty();
+            const int j = have ? q.pop_back() : 0;
             const unsigned int gi = (unsigned int)(c * WCHUNK + j);
             const float4* rp = r + j * TR::R4;
             bool valid = have && gi < last_contributor;

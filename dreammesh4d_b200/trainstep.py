@@ -57,19 +57,33 @@ class DynamicStageStep:
         geo = self.geo
         geo.update_step(0, step)
         self.opt.zero_grad(set_to_none=True)
-        total = None
-        for batch in batches:
-            ts = batch["timestamp"]
+        # The deformation network is evaluated ONCE per optimizer step for the timestamps of all substeps and
+        # back-propagated ONCE with the node-attribute gradients of all substeps: one HexPlane lookup / backward
+        # (one zero-fill of the 143 MB of plane gradients, no gradient accumulation passes) instead of one per substep.
+        ts_all = torch.cat([b["timestamp"] for b in batches])
+        single = not (dist.is_initialized() and dist.get_world_size(self.group) > 1)
+        if single:
+            live = geo.get_timed_dg_attributes(ts_all)             # autograd graph kept: no replay needed
+        else:
             with torch.no_grad():
-                node = geo.get_timed_dg_attributes(ts)
-            node = [None if t is None else t.detach().requires_grad_(True) for t in node]
+                live = geo.get_timed_dg_attributes(ts_all)
+        leaves = [None if t is None else t.detach().requires_grad_(True) for t in live]
+        total, off = None, 0
+        for batch in batches:
+            n = batch["timestamp"].shape[0]
+            node = [None if t is None else t[off:off + n] for t in leaves]
             out = self.ren.batch_forward(batch, node_attrs=node)
             loss = self.loss_fn(out, batch)
             loss.backward()                                    # ... down to the control-node attributes
-            node_attribute_backward(geo._deformation, geo._deform_graph_node_xyz, ts, [None if t is None else t.grad for t in node],
-                                    self.group)                # exchange + replicated network backward
             total = loss.detach() if total is None else total + loss.detach()
+            off += n
             geo.update_step(0, step)                           # per-substep caches (dynamic_sugar.py:863-873)
+        grads = [None if t is None else t.grad for t in leaves]
+        if single:
+            pairs = [(a, g) for a, g in zip(live, grads) if a is not None and g is not None]
+            torch.autograd.backward([a for a, _ in pairs], [g for _, g in pairs])
+        else:                                                  # exchange + replicated network backward
+            node_attribute_backward(geo._deformation, geo._deform_graph_node_xyz, ts_all, grads, self.group)
         self.opt.step()
         return total
 
