@@ -65,6 +65,23 @@ def _prep(t: torch.Tensor, k: int, name: str):
     raise ValueError(f"{name} must be [P,{k}] or [S,P,{k}], got {tuple(t.shape)}")
 
 
+class RasterWorkspace:
+    """Optional persistent scratch (geom / bin / img / bwd sections, grow-only) for callers that run
+    forward -> backward -> forward -> ... in stream order, e.g. a training loop or ``HostStreamedRasterStep``:
+    the GB-sized sections are then allocated once instead of once per call.  A workspace serves ONE forward at a
+    time: its backward must run before the next forward that uses the same workspace."""
+
+    def __init__(self):
+        self._t = {}
+
+    def get(self, name: str, nbytes: int, device) -> torch.Tensor:
+        t = self._t.get(name)
+        if t is None or t.numel() < nbytes or t.device != device:
+            t = torch.empty(int(nbytes * 1.1) + 256, dtype=torch.uint8, device=device)
+            self._t[name] = t
+        return t
+
+
 class RasterState:
     """Caller-owned scratch of one batch (kept alive for the backward)."""
 
@@ -96,7 +113,7 @@ class RasterState:
 class _RasterizeBatch(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, opacities, scales, rotations, colors, colors2, view_params, H, W,
-                capacity, distinct_sets, state_out):
+                capacity, distinct_sets, state_out, workspace):
         l = _lib.lib()
         dev = means3D.device
         if dev.type != "cuda":
@@ -140,6 +157,7 @@ class _RasterizeBatch(torch.autograd.Function):
             return g.value, b.value, i.value, w.value
 
         u8 = dict(dtype=torch.uint8, device=dev)
+        scratch = (lambda name, n: torch.empty(n, **u8)) if workspace is None else (lambda name, n: workspace.get(name, n, dev))
         radii = torch.empty(B, P, dtype=torch.int32, device=dev)
         color = torch.empty(B, channels, H, W, dtype=torch.float32, device=dev)
         depth = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
@@ -149,21 +167,21 @@ class _RasterizeBatch(torch.autograd.Function):
             # exact sizing with one host read-back of num_rendered, like the replaced rasterizer:
             # plan into a capacity-0 workspace to learn R, then run the forward at capacity R
             gb, bb, ib, wb = sizes(0)
-            geom, img, bin0 = torch.empty(gb, **u8), torch.empty(ib, **u8), torch.empty(bb, **u8)
+            geom, img, bin0 = scratch("geom", gb), scratch("img", ib), torch.empty(bb, **u8)
             d.geom, d.geom_bytes, d.img, d.img_bytes = ptr(geom), gb, ptr(img), ib
             d.bin, d.bin_bytes, d.bin_capacity = ptr(bin0), bb, 0
             n = ctypes.c_int64(0)
             check(l.dm4d_raster_plan(ctypes.byref(d), ptr(radii), ctypes.byref(n), stream), "dm4d_raster_plan")
             capacity = int(n.value)
             _, bb, _, _ = sizes(capacity)
-            bin_ = torch.empty(bb, **u8)
+            bin_ = scratch("bin", bb)
             d.bin, d.bin_bytes, d.bin_capacity = ptr(bin_), bb, capacity
             check(l.dm4d_raster_forward(ctypes.byref(d), ptr(color), ptr(depth), ptr(alpha), ptr(radii), stream),
                   "dm4d_raster_forward")
         else:
             capacity = int(capacity)
             gb, bb, ib, wb = sizes(capacity)
-            geom, bin_, img = torch.empty(gb, **u8), torch.empty(bb, **u8), torch.empty(ib, **u8)
+            geom, bin_, img = scratch("geom", gb), scratch("bin", bb), scratch("img", ib)
             d.geom, d.geom_bytes, d.img, d.img_bytes = ptr(geom), gb, ptr(img), ib
             d.bin, d.bin_bytes, d.bin_capacity = ptr(bin_), bb, capacity
             check(l.dm4d_raster_forward(ctypes.byref(d), ptr(color), ptr(depth), ptr(alpha), ptr(radii), stream),
@@ -171,6 +189,7 @@ class _RasterizeBatch(torch.autograd.Function):
 
         state = RasterState(d, [m, sc, ro, op, co, c2, vp, geom, bin_, img, alpha], capacity)
         ctx.state = state
+        ctx.workspace = workspace
         ctx.shapes = (means3D.shape, scales.shape, rotations.shape, opacities.shape, colors.shape,
                       None if colors2 is None else colors2.shape)
         ctx.has_means2D = means2D is not None
@@ -192,7 +211,8 @@ class _RasterizeBatch(torch.autograd.Function):
         check(l.dm4d_raster_workspace_bytes(d.P, d.H, d.W, d.n_views, d.channels, d.bin_capacity, ctypes.byref(g_),
                                             ctypes.byref(b_), ctypes.byref(i_), ctypes.byref(wb)),
               "dm4d_raster_workspace_bytes")
-        bwd = torch.empty(wb.value, dtype=torch.uint8, device=dev)
+        bwd = torch.empty(wb.value, dtype=torch.uint8, device=dev) if ctx.workspace is None else \
+            ctx.workspace.get("bwd", wb.value, dev)
         d.bwd, d.bwd_bytes = ptr(bwd), wb.value
 
         gC = g_color.contiguous().float()
@@ -214,11 +234,12 @@ class _RasterizeBatch(torch.autograd.Function):
         rs = lambda t, s: None if t is None else t.reshape(s)
         return (rs(d_means3D, sh[0]), d_means2D, rs(d_opac, sh[3]), rs(d_scales, sh[1]), rs(d_rots, sh[2]),
                 rs(d_colors, sh[4]), None if d_colors2 is None else rs(d_colors2, sh[5]),
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None)
 
 
 def rasterize_batch(means3D, opacities, scales, rotations, colors, view_params, H, W, colors2=None, means2D=None,
-                    capacity: Optional[int] = None, distinct_sets: bool = False, state_out: Optional[list] = None):
+                    capacity: Optional[int] = None, distinct_sets: bool = False, state_out: Optional[list] = None,
+                    workspace: Optional[RasterWorkspace] = None):
     """Rasterizes a batch of views in one launch sequence.
 
     Attributes are ``[P,k]`` (shared by all views) or ``[S,P,k]`` (one set per timestamp; each view picks
@@ -226,11 +247,12 @@ def rasterize_batch(means3D, opacities, scales, rotations, colors, view_params, 
     the screen-space mean gradient, as in the reference (``viewspace_points``,
     diff_sugar_rasterizer_temporal.py:108-113).  ``capacity=None`` sizes the binning workspace exactly
     with one host read-back (the replaced rasterizer's behaviour); an integer keeps the call fully
-    asynchronous (check ``state.status()`` for overflow).
+    asynchronous (check ``state.status()`` for overflow).  ``workspace``: optional persistent scratch
+    (``RasterWorkspace``) for strictly alternating forward/backward call sequences.
     Returns ``color [B,C,H,W], radii [B,P] int32, depth [B,1,H,W], alpha [B,1,H,W]``.
     """
     return _RasterizeBatch.apply(means3D, means2D, opacities, scales, rotations, colors, colors2, view_params,
-                                 int(H), int(W), capacity, distinct_sets, state_out)
+                                 int(H), int(W), capacity, distinct_sets, state_out, workspace)
 
 
 # --------------------------------------------------------------------------------------------

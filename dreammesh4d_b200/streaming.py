@@ -47,6 +47,9 @@ class HostStreamedRasterStep:
         self.inflight: deque = deque()
         self.retain_all = False                   # set while capturing into a CUDA graph (see run_many)
         self.last_state: Optional[R.RasterState] = None
+        # compute runs in stream order (forward i, backward i, forward i+1, ...): one persistent scratch serves all
+        # steps, so the eager path allocates no GB-sized blocks per step (the copy streams only touch outputs)
+        self.workspace = R.RasterWorkspace()
 
     def step(self) -> None:
         cur = torch.cuda.current_stream()
@@ -69,7 +72,7 @@ class HostStreamedRasterStep:
         st: list = []
         color, radii, depth, alpha = R.rasterize_batch(buf["means"], buf["opac"], buf["scales"], buf["rots"], buf["cols"],
                                                        self.vp, self.H, self.W, capacity=self.capacity, distinct_sets=True,
-                                                       state_out=st)
+                                                       state_out=st, workspace=self.workspace)
         torch.autograd.backward([color, depth, alpha], [buf["gC"], buf["gD"], buf["gA"]])
         self.last_state = st[0]
         grads = {n: buf[n].grad for n in self.hs}
