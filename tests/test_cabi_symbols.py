@@ -49,3 +49,22 @@ def test_no_cpu_fallback():
     z = lambda k: torch.zeros(4, k)
     with pytest.raises(Dm4dError):
         R.rasterize_batch(z(3), z(1), z(3), z(4), z(3), torch.zeros(1, 48), 16, 16)
+
+
+def test_no_cpu_fallback_in_the_widened_rows():
+    """Post-ops, HexPlane lookup and graph construction raise on CPU tensors instead of computing something else."""
+    import torch
+    from dreammesh4d_b200._lib import Dm4dError
+    from dreammesh4d_b200.deform_graph import knn_nodes
+    from dreammesh4d_b200.deformation import HexPlaneDeformation
+    from dreammesh4d_b200.postops import post_ops
+    with pytest.raises(Dm4dError):
+        post_ops(torch.zeros(1, 6, 8, 8), torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8), torch.zeros(1, 8, 8, 3),
+                 torch.zeros(1, 8, 8, 3))
+    with pytest.raises(Dm4dError):
+        HexPlaneDeformation(base_res=(4, 4, 4, 3), multires=(1,))(torch.zeros(5, 3), torch.tensor([0.5]))
+    with pytest.raises(Dm4dError):
+        knn_nodes(torch.zeros(4, 3), torch.zeros(3, 3), 2)
+    # the explicit PyTorch statement of the lookup stays available (A1 "stays PyTorch" in the north-star)
+    out = HexPlaneDeformation(base_res=(4, 4, 4, 3), multires=(1,), fused=False)(torch.zeros(5, 3), torch.tensor([0.5]))
+    assert out[0].shape == (1, 5, 3)

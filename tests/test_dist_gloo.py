@@ -84,3 +84,70 @@ def test_node_attribute_gradient_exchange_world2_gloo():
     port = 31500 + (os.getpid() % 2000)
     mp.spawn(_worker_nodegrad, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+class _StubGeometry:
+    """The slice of the geometry interface DynamicStageStep touches, around a real (PyTorch-lookup) deformation net."""
+
+    def __init__(self, net, xyz):
+        self._deformation, self._deform_graph_node_xyz = net, xyz
+
+    def update_step(self, *a, **k):
+        pass
+
+    def get_timed_dg_attributes(self, ts):
+        from dreammesh4d_b200.geometry import activate_node_deltas
+        return activate_node_deltas(*self._deformation(self._deform_graph_node_xyz, ts))
+
+
+class _StubRenderer:
+    """A differentiable stand-in for skinning + rasterizer + post-ops: any smooth function of the node attributes."""
+
+    def batch_forward(self, batch, node_attrs=None):
+        trans, rot, scale, opac = node_attrs
+        return {"x": (trans * batch["w"][:, None, None]).sum() + (rot ** 2 * batch["w"][:, None, None]).sum() +
+                     (scale.sum(dim=(-1, -2)) * batch["w"][:, None]).sum() * 0.1 + (opac[..., 0] * batch["w"][:, None]).sum()}
+
+
+def _make_net():
+    from dreammesh4d_b200.deformation import HexPlaneDeformation
+    torch.manual_seed(0)
+    net = HexPlaneDeformation(base_res=(8, 8, 8, 5), multires=(1, 2), fused=False)
+    with torch.no_grad():
+        for head in (net.deformation_net.pos_deform, net.deformation_net.rotations_deform,
+                     net.deformation_net.scales_deform, net.deformation_net.opacity_deform):
+            head.feature_out[1].weight.normal_(0, 0.1)
+    return net
+
+
+def _worker_step(rank, world, port, ret):
+    """DynamicStageStep with a process group: every rank steps on ITS batch; the parameters end up identical on all
+    ranks and equal to a single-process step over the union of the batches (the reference's DDP semantics)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from dreammesh4d_b200.trainstep import DynamicStageStep
+    xyz = torch.rand(7, 3, generator=torch.Generator().manual_seed(5)) - 0.5
+    g = torch.Generator().manual_seed(9)
+    batches = [{"timestamp": torch.rand(3, generator=g), "w": torch.randn(3, generator=g)} for _ in range(world)]
+    loss_fn = lambda out, b: out["x"]
+    # single-process reference over the union (no process group yet)
+    net_ref = _make_net()
+    DynamicStageStep(_StubGeometry(net_ref, xyz), _StubRenderer(), torch.optim.SGD(net_ref.parameters(), lr=0.1), loss_fn)(batches, 0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        net = _make_net()
+        step = DynamicStageStep(_StubGeometry(net, xyz), _StubRenderer(), torch.optim.SGD(net.parameters(), lr=0.1), loss_fn)
+        step([batches[rank]], 0)
+        moved = sum(float((p - q).abs().max()) > 0 for p, q in zip(net.parameters(), _make_net().parameters()))
+        same = all(torch.allclose(p, q, rtol=1e-5, atol=1e-7) for p, q in zip(net.parameters(), net_ref.parameters()))
+        ret[rank] = bool(same and moved >= 8)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_dynamic_stage_step_world2_gloo_equals_single_process_union():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_worker_step, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
