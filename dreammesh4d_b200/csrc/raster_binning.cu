@@ -445,6 +445,9 @@ __global__ void export_state_kernel(RasterLayout L, int view, unsigned int* rang
 
 }  // namespace
 
+#ifndef DM4D_SORT_SMALL_THREADS
+#define DM4D_SORT_SMALL_THREADS 128      // CTA size of the small-segment instantiation (8 keys per thread)
+#endif
 template <int R4>
 int launch_sort_pack_t(const RasterLayout& L, cudaStream_t s) {
     static bool configured = false;
@@ -454,8 +457,9 @@ int launch_sort_pack_t(const RasterLayout& L, cudaStream_t s) {
         configured = true;
     }
     const unsigned grid = (unsigned)(L.n_views * L.tiles);
-    sort_pack_kernel<SORT_THREADS, SORT_CHUNK, R4><<<grid, SORT_THREADS, smem, s>>>(L, 1024, 0x7fffffff);
-    sort_pack_kernel<128, 1024, R4><<<grid, 128, 1024 * sizeof(unsigned long long), s>>>(L, 0, 1024);
+    constexpr int SMALL_KEYS = MS_E * DM4D_SORT_SMALL_THREADS;
+    sort_pack_kernel<SORT_THREADS, SORT_CHUNK, R4><<<grid, SORT_THREADS, smem, s>>>(L, SMALL_KEYS, 0x7fffffff);
+    sort_pack_kernel<DM4D_SORT_SMALL_THREADS, SMALL_KEYS, R4><<<grid, DM4D_SORT_SMALL_THREADS, SMALL_KEYS * sizeof(unsigned long long), s>>>(L, 0, SMALL_KEYS);
     return DM4D_OK;
 }
 
