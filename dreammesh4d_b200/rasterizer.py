@@ -273,6 +273,41 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
+_SH_C0 = 0.28209479177387814
+_SH_C1 = 0.4886025119029199
+_SH_C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
+_SH_C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435)
+
+
+def sh_to_rgb(shs: torch.Tensor, means3D: torch.Tensor, campos: torch.Tensor, degree: int) -> torch.Tensor:
+    """View-dependent colour from real spherical harmonics, the convention of the replaced rasterizer's preprocess
+    (SURVEY.md Appendix A.2 step 8): ``shs [P, >= (degree+1)^2, 3]``, direction ``(p - campos) / |p - campos|``,
+    ``rgb = max(0, SH(dir) + 0.5)`` (the clamp passes no gradient where it acts).  Degree 0 is
+    ``SH2RGB`` of the reference (geometry/gaussian_base.py:39-40) followed by the clamp."""
+    if degree < 0 or degree > 3:
+        raise ValueError("sh_degree must be 0..3")
+    if shs.dim() != 3 or shs.shape[-1] != 3 or shs.shape[1] < (degree + 1) ** 2:
+        raise ValueError(f"shs must be [P, >= {(degree + 1) ** 2}, 3], got {tuple(shs.shape)}")
+    sh = shs.unbind(dim=1)
+    res = _SH_C0 * sh[0]
+    if degree > 0:
+        d = means3D - campos.reshape(1, 3).to(means3D)
+        d = d / d.norm(dim=-1, keepdim=True)
+        x, y, z = d[:, 0:1], d[:, 1:2], d[:, 2:3]
+        res = res - _SH_C1 * y * sh[1] + _SH_C1 * z * sh[2] - _SH_C1 * x * sh[3]
+        if degree > 1:
+            xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+            res = res + _SH_C2[0] * xy * sh[4] + _SH_C2[1] * yz * sh[5] + _SH_C2[2] * (2.0 * zz - xx - yy) * sh[6] + \
+                _SH_C2[3] * xz * sh[7] + _SH_C2[4] * (xx - yy) * sh[8]
+            if degree > 2:
+                res = res + _SH_C3[0] * y * (3.0 * xx - yy) * sh[9] + _SH_C3[1] * xy * z * sh[10] + \
+                    _SH_C3[2] * y * (4.0 * zz - xx - yy) * sh[11] + _SH_C3[3] * z * (2.0 * zz - 3.0 * xx - 3.0 * yy) * sh[12] + \
+                    _SH_C3[4] * x * (4.0 * zz - xx - yy) * sh[13] + _SH_C3[5] * z * (xx - yy) * sh[14] + \
+                    _SH_C3[6] * x * (xx - 3.0 * yy) * sh[15]
+    return torch.clamp_min(res + 0.5, 0.0)
+
+
 class GaussianRasterizer(nn.Module):
     """Same constructor/forward signature and 4-tuple return as the replaced module."""
 
@@ -292,8 +327,10 @@ class GaussianRasterizer(nn.Module):
             raise NotImplementedError("cov3D_precomp is not on the DreamMesh4D hot path "
                                       "(the plugin always passes scales/rotations; DESIGN.md §7)")
         if shs is not None:
-            raise NotImplementedError("SH evaluation inside the rasterizer is not on the DreamMesh4D hot path "
-                                      "(both systems pass colors_precomp; DESIGN.md §7)")
+            # SH -> RGB as the replaced module does it in its preprocess (computeColorFromSH): evaluated here with device
+            # tensor ops, then rasterized as precomputed colours.  Reached by the reference only in predict_step
+            # (system/base.py:257, degree 0); autograd supplies the gradients incl. the view-direction term.
+            colors_precomp = sh_to_rgb(shs, means3D, rs.campos, int(rs.sh_degree))
         vp = make_view_params(rs.viewmatrix.reshape(1, 4, 4), rs.projmatrix.reshape(1, 4, 4),
                               rs.campos.reshape(1, 3), rs.tanfovx, rs.tanfovy, rs.bg.reshape(1, -1)[:, :3],
                               rs.scale_modifier)

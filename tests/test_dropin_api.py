@@ -53,3 +53,37 @@ def test_argument_validation_matches_the_replaced_module():
         r(means3D=z(3), means2D=z(3), opacities=z(1), colors_precomp=z(3))
     with pytest.raises(NotImplementedError):
         r(means3D=z(3), means2D=z(3), opacities=z(1), colors_precomp=z(3), cov3D_precomp=torch.zeros(4, 6))
+
+
+def test_sh_to_rgb_degree0_is_the_reference_sh2rgb_and_bands_are_orthonormal():
+    """``shs=`` path of the drop-in module (reached by the reference's predict_step with degree 0): degree 0 equals the
+    reference's SH2RGB (geometry/gaussian_base.py:39-40: sh * 0.28209479177387814 + 0.5) with the rasterizer's clamp at 0;
+    for degrees 1..3 the 16 basis functions are orthonormal on the sphere (constants and polynomials are consistent)."""
+    import math
+    from dreammesh4d_b200.rasterizer import sh_to_rgb
+    g = torch.Generator().manual_seed(0)
+    sh = torch.randn(50, 1, 3, generator=g, dtype=torch.float64)
+    p = torch.randn(50, 3, generator=g, dtype=torch.float64)
+    want = (sh[:, 0] * 0.28209479177387814 + 0.5).clamp_min(0)
+    assert torch.allclose(sh_to_rgb(sh, p, torch.zeros(3, dtype=torch.float64), 0), want, atol=1e-15)
+    # basis functions: unit coefficient on one band, colour - 0.5 without the clamp acting (scale the coefficient down)
+    n = 200_000
+    i = torch.arange(n, dtype=torch.float64) + 0.5
+    phi, z = math.pi * (1 + 5 ** 0.5) * i, 1 - 2 * i / n                      # Fibonacci sphere: equal-area quadrature
+    r = torch.sqrt(1 - z * z)
+    dirs = torch.stack([r * torch.cos(phi), r * torch.sin(phi), z], dim=-1)
+    Y = []
+    for k in range(16):
+        c = torch.zeros(n, 16, 3, dtype=torch.float64)
+        c[:, k, :] = 0.1
+        Y.append((sh_to_rgb(c, dirs, torch.zeros(3, dtype=torch.float64), 3)[:, 0] - 0.5) / 0.1)
+    Y = torch.stack(Y, dim=1)                                                 # [n,16]
+    gram = (Y.t() @ Y) * (4 * math.pi / n)
+    assert (gram - torch.eye(16, dtype=torch.float64)).abs().max() < 2e-3
+    # gradients flow to the coefficients and (degree > 0) to the positions; the clamp blocks them where it acts
+    c = torch.randn(20, 16, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    q = torch.randn(20, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    out = sh_to_rgb(c, q, torch.tensor([0.1, -0.2, 3.0], dtype=torch.float64), 3)
+    out.sum().backward()
+    assert q.grad.abs().max() > 0 and c.grad.abs().max() > 0
+    assert bool((c.grad[:, 0][out == 0] == 0).all())

@@ -227,3 +227,27 @@ def test_host_streamed_step_matches_direct_call():
     assert torch.equal(step.out["color"], color.detach().cpu()) and torch.equal(step.out["alpha"], alpha.detach().cpu())
     for name, ref in (("means", dm), ("rots", dr), ("scales", ds), ("opac", do), ("cols", dc)):
         assert Hh.rel_linf(step.out[name].numpy(), ref.grad.cpu().numpy()) <= 1e-5, name
+
+
+def test_dropin_shs_path_equals_precomputed_colours():
+    """``shs=`` (the reference's predict_step, degree 0; here also degree 2): colours evaluated by sh_to_rgb on the device
+    and rasterized — identical to passing the same colours as colors_precomp, and gradients reach the coefficients."""
+    P, H, W = 2000, 64, 80
+    means, scales, rots, opac, cols = Hh.random_scene(P, 5)
+    V, PV, campos, tanx, tany = Hh.cameras(1, seed=3)
+    bg = torch.ones(3)
+    for deg in (0, 2):
+        g = torch.Generator().manual_seed(deg)
+        shs = (torch.randn(P, (deg + 1) ** 2, 3, generator=g) * 0.5).to(DEV).requires_grad_(True)
+        settings = R.GaussianRasterizationSettings(H, W, float(tanx[0]), float(tany[0]), bg.to(DEV), 1.0, V[0].to(DEV),
+                                                   PV[0].to(DEV), deg, campos[0].to(DEV), False, False)
+        rast = R.GaussianRasterizer(settings)
+        d = lambda x: x.to(DEV)
+        c1, r1, d1, a1 = rast(means3D=d(means), means2D=torch.zeros(P, 3, device=DEV), opacities=d(opac), shs=shs,
+                              scales=d(scales), rotations=d(rots))
+        pre = R.sh_to_rgb(shs.detach(), d(means), campos[0].to(DEV), deg)
+        c2, r2, d2, a2 = rast(means3D=d(means), means2D=torch.zeros(P, 3, device=DEV), opacities=d(opac), colors_precomp=pre,
+                              scales=d(scales), rotations=d(rots))
+        assert torch.equal(c1, c2) and torch.equal(r1, r2) and torch.equal(d1, d2) and torch.equal(a1, a2)
+        c1.sum().backward()
+        assert shs.grad is not None and float(shs.grad.abs().max()) > 0
