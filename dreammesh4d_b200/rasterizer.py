@@ -315,6 +315,13 @@ class GaussianRasterizer(nn.Module):
         super().__init__()
         self.raster_settings = raster_settings
 
+    def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
+        """Frustum test of the replaced module (``mark_visible`` -> in_frustum): view-space depth > 0.2 (SURVEY.md
+        Appendix A.2 step 1).  Not called by the reference; part of the module's public surface."""
+        with torch.no_grad():
+            V = self.raster_settings.viewmatrix.to(positions)        # transposed (row-vector) world->view matrix
+            return positions @ V[:3, 2] + V[3, 2] > 0.2
+
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                 cov3D_precomp=None):
         rs = self.raster_settings

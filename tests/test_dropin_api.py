@@ -87,3 +87,15 @@ def test_sh_to_rgb_degree0_is_the_reference_sh2rgb_and_bands_are_orthonormal():
     out.sum().backward()
     assert q.grad.abs().max() > 0 and c.grad.abs().max() > 0
     assert bool((c.grad[:, 0][out == 0] == 0).all())
+
+
+def test_mark_visible_is_the_near_plane_test():
+    from dreammesh4d_b200 import synthetic
+    from dreammesh4d_b200.camera import get_cam_info_gaussian
+    mod = _shim()
+    c2w, fovy = synthetic.random_orbit_cameras(1, seed=4)
+    V, PV, campos, tanx, tany = get_cam_info_gaussian(c2w, fovy, fovy)
+    s = mod.GaussianRasterizationSettings(8, 8, float(tanx[0]), float(tany[0]), torch.ones(3), 1.0, V[0], PV[0], 0, campos[0], False, False)
+    look = -campos[0] / campos[0].norm()
+    pts = torch.stack([campos[0] + 0.1 * look, campos[0] + 0.3 * look, campos[0] - 1.0 * look, torch.zeros(3)])
+    assert mod.GaussianRasterizer(s).markVisible(pts).tolist() == [False, True, False, True]
