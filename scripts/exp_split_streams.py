@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""EXPERIMENT (not product code, not yet run on a GPU): overlap the latency-bound kernels of one half of a step's views
+"""EXPERIMENT (not product code; first attempt failed on a capture detail, fixed but not re-run — no GPU budget left): overlap the latency-bound kernels of one half of a step's views
 (preprocess, scan, scatter, tile sort, preprocess backward: ~0.65 ms of the 2.06 ms step at C3, issue slots ~50 % busy)
 with the issue-bound render kernels of the other half, by rasterizing the two halves of the view batch through the
 public API on two streams and capturing both into one CUDA graph (a forked graph).  Prints ms/step of the single
@@ -40,6 +40,7 @@ def main():
     vps = [vp_for(gr) for gr in groups]
     vp_all = vp_for(list(range(VIEWS)))
     streams = [torch.cuda.Stream() for _ in groups]
+    ixs = [torch.tensor(gr, device=dev) for gr in groups]        # built outside the capture (no pageable H2D inside a graph)
 
     def one_call():
         c, _, d, a = R.rasterize_batch(inp["means3D"], inp["opacities"], inp["scales"], inp["rotations"], inp["colors"],
@@ -50,10 +51,9 @@ def main():
 
     def split_call():
         cur = torch.cuda.current_stream()
-        for s, gr, vp in zip(streams, groups, vps):
+        for s, ix, vp in zip(streams, ixs, vps):
             s.wait_stream(cur)
             with torch.cuda.stream(s):
-                ix = torch.tensor(gr, device=dev)
                 m, r = inp["means3D"].detach()[ix].requires_grad_(True), inp["rotations"].detach()[ix].requires_grad_(True)
                 sh = [inp[k].detach().requires_grad_(True) for k in ("opacities", "scales", "colors")]
                 c, _, d, a = R.rasterize_batch(m, sh[0], sh[1], r, sh[2], vp, H, W, capacity=cap, distinct_sets=True)
