@@ -332,7 +332,7 @@ class GaussianRasterizer(nn.Module):
             raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
         if cov3D_precomp is not None:
             raise NotImplementedError("cov3D_precomp is not on the DreamMesh4D hot path "
-                                      "(the plugin always passes scales/rotations; DESIGN.md §7)")
+                                      "(the plugin always passes scales/rotations; DESIGN.md §2)")
         if shs is not None:
             # SH -> RGB as the replaced module does it in its preprocess (computeColorFromSH): evaluated here with device
             # tensor ops, then rasterized as precomputed colours.  Reached by the reference only in predict_step
