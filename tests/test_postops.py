@@ -104,3 +104,27 @@ def test_postops_kernels_on_golden_inputs(tag):
     assert Hh.rel_linf(g6[0, 3:].cpu().double(), t["grad_nrm"]) <= Hh.TOL_GRAD
     assert Hh.rel_linf(gd[0].cpu().double(), t["grad_depth"]) <= Hh.TOL_GRAD
     assert Hh.rel_linf(ga[0].cpu().double(), t["grad_alpha"]) <= Hh.TOL_GRAD
+
+
+@pytest.mark.gpu
+def test_postops_without_normal_from_dist_is_consistent():
+    """compute_normal_from_dist=False (no rays in the batch): same images, and the same gradients as the full call
+    when the normal-from-distance output receives no gradient."""
+    from dreammesh4d_b200 import postops
+    rgb, nrm, depth, alpha, rays_o, rays_d = _gpu_case(2, 40, 56, seed=11)
+    d = lambda x: x.float().cuda()
+    mk = lambda: (d(torch.cat([rgb, nrm], dim=1)).requires_grad_(True), d(depth).requires_grad_(True), d(alpha).requires_grad_(True))
+    g = torch.Generator().manual_seed(3)
+    cot = {k: torch.randn(2, 40, 56, c, generator=g).cuda() for k, c in
+           (("comp_rgb", 3), ("comp_normal", 3), ("comp_depth", 1), ("comp_mask", 1))}
+    a6, ad, aa = mk()
+    full = postops.post_ops(a6, ad, aa, d(rays_o), d(rays_d))
+    b6, bd, ba = mk()
+    lite = postops.post_ops(b6, bd, ba, compute_normal_from_dist=False)
+    assert "comp_normal_from_dist" not in lite
+    for k in cot:
+        assert torch.equal(full[k], lite[k]), k
+    ga = torch.autograd.grad(sum((full[k] * cot[k]).sum() for k in cot), (a6, ad, aa))
+    gb = torch.autograd.grad(sum((lite[k] * cot[k]).sum() for k in cot), (b6, bd, ba))
+    for x, y in zip(ga, gb):
+        assert torch.allclose(x, y, rtol=0, atol=1e-6 * float(x.abs().max()))
