@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_int32, c_int64, c_uint64, c_void_p
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent

@@ -8,7 +8,6 @@ timestamps of a step in one launch sequence.
 from __future__ import annotations
 
 import ctypes
-from typing import Optional
 
 import torch
 

@@ -4,7 +4,6 @@ provided by dreammesh4d_b200/shims and accepts exactly the call shapes the refer
 import importlib
 import inspect
 import json
-import sys
 from pathlib import Path
 
 import pytest

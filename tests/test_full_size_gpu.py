@@ -14,9 +14,8 @@ import pytest
 import torch
 
 from dreammesh4d_b200 import rasterizer as R
-from dreammesh4d_b200 import skinning, synthetic
+from dreammesh4d_b200 import synthetic
 from oracle import skin_oracle as SO
-from oracle.raster_oracle import RasterOracle
 from tests import helpers as Hh
 from tests.test_raster_parity_gpu import check_view, run_oracle
 from tests.test_skin_parity_gpu import run_both

@@ -2,7 +2,6 @@
 (DiffGaussianBatchRenderer.batch_forward) against the oracle chain (CPU copy of the network -> skin oracle ->
 C rasterizer oracle per view -> the same post-ops restated in torch), forward and full-chain gradients."""
 import copy
-import math
 
 import numpy as np
 import pytest
