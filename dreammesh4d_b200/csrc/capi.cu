@@ -16,7 +16,7 @@ void dm4d_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* dm4d_last_error(void) { return g_err; }
-extern "C" int dm4d_version(void) { return 100; }
+extern "C" int dm4d_version(void) { return 110; }   // 1.1: + postops, hexplane, graph_knn
 
 void raster_sizes(int P, int H, int W, int n_views, int channels, long long capacity, uint64_t* geom, uint64_t* bin,
                   uint64_t* img, uint64_t* bwd) {
