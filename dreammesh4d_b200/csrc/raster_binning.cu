@@ -288,7 +288,7 @@ __device__ __forceinline__ unsigned int cell_mask(const float4 a, const float4 b
         const float cx = a.z, cy = a.w, cz = b.x;
         const float det = cx * cz - cy * cy;
         if (!(cx > 0.f) || !(cz > 0.f) || !(det > 0.f) || !(thr < 1e29f)) {
-            mask = 0xffffu;
+            mask = DM4D_CELL_ROWS == 4 ? 0xffffu : 0xffffffffu;
         } else {
             const float icx = 1.f / cx, idet = 1.f / det;
             const float X = sqrt_approx(thr * cz * idet), Y = sqrt_approx(thr * cx * idet);   // half extents of E
@@ -297,9 +297,10 @@ __device__ __forceinline__ unsigned int cell_mask(const float4 a, const float4 b
             float x0[4];                                   // left edges of the cell columns (pixel - centre, with margin)
 #pragma unroll
             for (int i = 0; i < 4; ++i) x0[i] = tile_x0 + (float)(4 * i) - a.x - 0.01f;
+            constexpr int CR = DM4D_CELL_ROWS;                              // cell height: 4 (16-bit mask) or 2 (32-bit mask)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float y0 = tile_y0 + (float)(4 * j) - a.y - 0.01f, y1 = y0 + 3.02f;
+            for (int j = 0; j < 16 / CR; ++j) {
+                const float y0 = tile_y0 + (float)(CR * j) - a.y - 0.01f, y1 = y0 + (CR == 4 ? 3.02f : 1.02f);
                 if (y0 > Y || y1 < -Y) continue;                                   // the strip misses E
                 const float ya = fminf(fmaxf(y0, -Y), Y), yb = fminf(fmaxf(y1, -Y), Y);
                 const float da = sqrt_approx(fmaxf(tcx - det * ya * ya, 0.f)), db = sqrt_approx(fmaxf(tcx - det * yb * yb, 0.f));

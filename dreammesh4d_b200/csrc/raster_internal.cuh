@@ -6,6 +6,14 @@
 
 #define DM4D_BLOCK 256
 
+// Height of a culling cell (cells are 4 pixels wide).  4 (default, validated): 4x4 cells, one instance queue per
+// HALF-warp, 16-bit masks.  2 (EXPERIMENTAL, prepared at the end of round 1 and not yet run on a GPU): 4x2 cells, one
+// queue per QUARTER-warp, 32-bit masks — 1.07 instead of 1.21 warp iterations per instance in the CPU simulation
+// (scripts/sim_cell_queues.py).  raster_binning.cu (mask) and raster_render.cu (queues, reductions) must agree.
+#ifndef DM4D_CELL_ROWS
+#define DM4D_CELL_ROWS 4
+#endif
+
 struct BinHeader {
     unsigned long long total;   // R = number of (Gaussian, tile) instances over all views
     unsigned int overflow;      // 1 if R > capacity (nothing rendered)

@@ -69,6 +69,7 @@ __device__ __forceinline__ float fast_rcp(float x) {
     return r;
 }
 
+#if DM4D_CELL_ROWS == 4
 // Pixel owned by a thread: warp w covers the 8x4 block (w & 1, w >> 1); its half-warp h covers the 4x4 cell
 // (cx, cy) = (2 (w & 1) + h, w >> 1), whose bit in an instance's cell mask is cy * 4 + cx = 2 w + h.
 struct PixelMap {
@@ -81,6 +82,22 @@ struct PixelMap {
         cell_bit = 2 * warp + half;
     }
 };
+#else
+// EXPERIMENTAL 4x2 cells: warp w covers the 8x4 block (w & 1, w >> 1); its quarter-warp g = lane / 8 covers the 4x2
+// cell (cx, cy8) = (2 (w & 1) + (g & 1), 2 (w >> 1) + (g >> 1)) of the tile's 4 x 8 cells; mask bit 4 cy8 + cx.
+// `half` holds the group index g, `li` the lane within the group (0..7).
+struct PixelMap {
+    int px, py, cell_bit, half, li;
+    __device__ __forceinline__ PixelMap(int tile_x, int tile_y, int warp, int lane) {
+        half = lane >> 3;
+        li = lane & 7;
+        const int cx = ((warp & 1) << 1) | (half & 1), cy8 = ((warp >> 1) << 1) | (half >> 1);
+        px = tile_x * DM4D_TILE + (cx << 2) + (li & 3);
+        py = tile_y * DM4D_TILE + (cy8 << 1) + (li >> 2);
+        cell_bit = 4 * cy8 + cx;
+    }
+};
+#endif
 
 // Candidate queue of this lane's half-warp for one staged chunk of 64 instances: bit j set <=> instance j of the chunk
 // can reach the half-warp's cell.  Four warp ballots (two cells x two 32-instance groups); uniform within a half-warp.
@@ -109,6 +126,7 @@ struct CellQueue {
     }
 };
 
+#if DM4D_CELL_ROWS == 4
 template <int R4>
 __device__ __forceinline__ CellQueue cell_queue(const float4* r, int cnt, int lane, int warp, int half) {
     const unsigned int m0 = lane < cnt ? __float_as_uint(r[lane * R4 + 1].z) : 0u;
@@ -121,6 +139,23 @@ __device__ __forceinline__ CellQueue cell_queue(const float4* r, int cnt, int la
     q.hi = half ? b1 : a1;
     return q;
 }
+#else
+// EXPERIMENTAL 4x2 cells: four queues per warp (one per quarter-warp), eight ballots per chunk.
+template <int R4>
+__device__ __forceinline__ CellQueue cell_queue(const float4* r, int cnt, int lane, int warp, int grp) {
+    const unsigned int m0 = lane < cnt ? __float_as_uint(r[lane * R4 + 1].z) : 0u;
+    const unsigned int m1 = lane + 32 < cnt ? __float_as_uint(r[(lane + 32) * R4 + 1].z) : 0u;
+    CellQueue q;
+    q.lo = q.hi = 0u;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int bit = 4 * ((((warp >> 1) << 1) | (g >> 1))) + (((warp & 1) << 1) | (g & 1));
+        const unsigned int lo = __ballot_sync(0xffffffffu, (m0 >> bit) & 1u), hi = __ballot_sync(0xffffffffu, (m1 >> bit) & 1u);
+        if (g == grp) { q.lo = lo; q.hi = hi; }
+    }
+    return q;
+}
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -374,6 +409,57 @@ __device__ __forceinline__ int slot_of10(int li) {
     return (t <= 2 && u <= 4) ? ((li & 8) ? 5 : 0) + u : -1;
 }
 
+#if DM4D_CELL_ROWS == 2
+// EXPERIMENTAL quarter-warp (8 lanes, xor distances 4, 2, 1) reductions: every lane ends with up to TWO slots.
+// N = 10: 10 -> 5 -> 3 -> 2 with 5 + 3 + 2 = 10 shuffles; lane li (bits b2 b1 b0) holds out[k], k = 0, 1, for slot
+// 5 b2 + 3 b1 + (2 b0 + k) when 2 b0 + k <= 2 and 3 b1 + 2 b0 + k <= 4 (quarter_slot10), else padding.
+__device__ __forceinline__ void quarter_reduce_scatter10(float (&v)[10], int li, float (&out)[2]) {
+    const bool b2 = li & 4, b1 = li & 2, b0 = li & 1;
+    float w[6], x[4];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float send = b2 ? v[i] : v[i + 5], keep = b2 ? v[i + 5] : v[i];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    w[5] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float send = b1 ? w[i] : w[i + 3], keep = b1 ? w[i + 3] : w[i];
+        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    x[3] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b0 ? x[i] : x[i + 2], keep = b0 ? x[i + 2] : x[i];
+        out[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+}
+__device__ __forceinline__ int quarter_slot10(int li, int k) {
+    const int t = ((li & 1) ? 2 : 0) + k, u = ((li & 2) ? 3 : 0) + t;
+    return (t <= 2 && u <= 4) ? ((li & 4) ? 5 : 0) + u : -1;
+}
+// N = 16: 16 -> 8 -> 4 -> 2 with 8 + 4 + 2 = 14 shuffles; lane li holds slots 2 li and 2 li + 1.
+__device__ __forceinline__ void quarter_reduce_scatter16(float (&v)[16], int li, float (&out)[2]) {
+    const bool b2 = li & 4, b1 = li & 2, b0 = li & 1;
+    float w8[8], w4[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = b2 ? v[i] : v[i + 8], keep = b2 ? v[i + 8] : v[i];
+        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b1 ? w8[i] : w8[i + 4], keep = b1 ? w8[i + 4] : w8[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b0 ? w4[i] : w4[i + 2], keep = b0 ? w4[i + 2] : w4[i];
+        out[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+}
+#endif
+
 template <int C>
 __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_kernel(RasterLayout L, const float* __restrict__ view_params,
                                                                    const float* __restrict__ out_alpha,
@@ -432,6 +518,7 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
     const float ddelx_dx = 0.5f * (float)L.W, ddely_dy = 0.5f * (float)L.H;
     float* accum_view = L.accum + (size_t)v * L.P * TR::ACC;
     // accumulator-row offset this lane adds its reduced slot to (rows: raster_internal.cuh); -1 = idle lane
+#if DM4D_CELL_ROWS == 4
     int acc_off;
     if constexpr (C <= 3) {
         const int sl = slot_of10(pm.li);          // reduction slots 0..6 = row 0..6, slots 7..9 = features at row 8..10
@@ -440,6 +527,20 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
         acc_off = (pm.li != 7 && pm.li < 8 + C) ? pm.li : -1;
     }
     const unsigned int half_lanes = 0xffffu << (pm.half * 16);
+#else
+    int acc_off2[2];                              // EXPERIMENTAL: two reduced slots per lane of a quarter-warp
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if constexpr (C <= 3) {
+            const int sl = quarter_slot10(pm.li, k);
+            acc_off2[k] = sl < 0 ? -1 : (sl < 7 ? sl : sl + 1);
+        } else {
+            const int sl = 2 * pm.li + k;         // lane li of the 16 -> 8 -> 4 -> 2 halving holds slots 2 li, 2 li + 1
+            acc_off2[k] = (sl != 7 && sl < 8 + C) ? sl : -1;
+        }
+    }
+    const unsigned int half_lanes = 0xffu << (pm.half * 8);
+#endif
 
     for (int k = 0; k < nchunks; ++k) {
         const int c = nchunks - 1 - k;
@@ -513,6 +614,7 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
                 gv[4] = hy * dy;
                 gv[5] = G * dL_dalpha;
             }
+#if DM4D_CELL_ROWS == 4
             float tot;
             if constexpr (C <= 3) tot = half_reduce_scatter10(gv, pm.li);
             else tot = half_reduce_scatter16(gv, pm.li);
@@ -521,6 +623,16 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
                 const int id = __float_as_int(rp[1].w);
                 atomicAdd(accum_view + (size_t)id * TR::ACC + acc_off, tot);
             }
+#else
+            float tot2[2];
+            if constexpr (C <= 3) quarter_reduce_scatter10(gv, pm.li, tot2);
+            else quarter_reduce_scatter16(gv, pm.li, tot2);
+            if (vb & half_lanes) {                // this quarter-warp's instance had a contributing lane
+                float* row = accum_view + (size_t)__float_as_int(rp[1].w) * TR::ACC;
+                if (acc_off2[0] >= 0) atomicAdd(row + acc_off2[0], tot2[0]);
+                if (acc_off2[1] >= 0) atomicAdd(row + acc_off2[1], tot2[1]);
+            }
+#endif
         }
         __syncwarp();
         if (lane == 0 && k + WSTAGES < nchunks) ring.issue(nchunks - 1 - (k + WSTAGES), sl);
