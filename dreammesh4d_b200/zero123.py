@@ -1,0 +1,527 @@
+"""Zero123 denoiser + first-stage encoder for the SDS stage of the hot path.
+
+The reference instantiates ``extern.ldm_zero123.models.diffusion.ddpm.LatentDiffusion`` from
+``load/zero123/sd-objaverse-finetune-c_concat-256.yaml`` (guidance/temporal_stable_zero123_guidance.py:41-73,106-117)
+and touches it per optimizer step through exactly three calls:
+
+  * ``encode_first_stage`` + ``get_first_stage_encoding``  (:228-236; AutoencoderKL encoder + quant_conv, gradient ON),
+  * ``cc_projection``                                       (:276-284; Linear 772 -> 768 on [CLIP embedding, camera delta]),
+  * ``apply_model``                                         (:342; DiffusionWrapper 'hybrid': concat c_concat on the channel
+                                                             axis, c_crossattn as the transformer context, UNetModel).
+
+This module is a from-scratch implementation of those three for B200: tensor-core matmuls through PyTorch (north-star:
+"the Zero123 UNet SDS step runs as PyTorch tensor-core matmuls"), channels-last activations so the 1x1 projections and
+the token reshapes of the transformer blocks are free views, fused scaled-dot-product attention, and the exact
+single-token shortcut for the cross-attention (Zero123's context is ONE token, so softmax == 1 and the attention output
+is ``to_out(to_v(context))`` broadcast over the pixels — q/k projections and the attention product are skipped).
+
+Checkpoint compatibility: parameter names and shapes are those of the reference modules, so the state_dict of
+``UNetModel`` (extern/ldm_zero123/modules/diffusionmodules/openaimodel.py:429-842), ``Encoder``
+(.../diffusionmodules/model.py:380-495) and the ``LatentDiffusion`` prefixes ``model.diffusion_model.`` /
+``first_stage_model.`` / ``cc_projection.`` load with ``strict=True`` (tests/test_zero123.py pins this against the
+reference's own classes executed at reduced width).  No weights are shipped: offline the model is random-initialised
+at the YAML's shapes (the FLOPs and the memory traffic of the step are those of the real model).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# configuration (load/zero123/sd-objaverse-finetune-c_concat-256.yaml:28-60)
+# --------------------------------------------------------------------------------------------------------------------
+@dataclass
+class UNetConfig:
+    in_channels: int = 8
+    out_channels: int = 4
+    model_channels: int = 320
+    attention_resolutions: Tuple[int, ...] = (4, 2, 1)
+    num_res_blocks: int = 2
+    channel_mult: Tuple[int, ...] = (1, 2, 4, 4)
+    num_heads: int = 8
+    context_dim: int = 768
+    groups: int = 32
+
+
+@dataclass
+class EncoderConfig:
+    in_channels: int = 3
+    ch: int = 128
+    ch_mult: Tuple[int, ...] = (1, 2, 4, 4)
+    num_res_blocks: int = 2
+    z_channels: int = 4
+    embed_dim: int = 4
+    groups: int = 32
+
+
+@dataclass
+class Zero123Config:
+    unet: UNetConfig = field(default_factory=UNetConfig)
+    encoder: EncoderConfig = field(default_factory=EncoderConfig)
+    scale_factor: float = 0.18215
+    timesteps: int = 1000
+    linear_start: float = 0.00085
+    linear_end: float = 0.0120
+    cc_in: int = 772            # 768 CLIP + 4 camera-delta entries (ddpm.py:653)
+    cc_out: int = 768
+
+
+class Slots(nn.Module):
+    """Children registered under explicit integer names: parameter keys equal those of the reference's
+    ``nn.Sequential`` containers without instantiating their parameter-free members (SiLU, Dropout, Identity)."""
+
+    def __init__(self, mods: Dict[int, nn.Module]):
+        super().__init__()
+        for i, m in mods.items():
+            self.add_module(str(i), m)
+
+    def __getitem__(self, i: int) -> nn.Module:
+        return self._modules[str(i)]
+
+
+def _pointwise(conv: nn.Conv2d, x_nhwc: torch.Tensor) -> torch.Tensor:
+    """1x1 convolution applied to a channels-last activation as a plain matmul over the last axis."""
+    return F.linear(x_nhwc, conv.weight.flatten(1), conv.bias)
+
+
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] (channels-last strides) -> [B,H,W,C] view."""
+    return x.permute(0, 2, 3, 1)
+
+
+def _nchw(x: torch.Tensor) -> torch.Tensor:
+    return x.permute(0, 3, 1, 2)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# UNet (openaimodel.py:429-842 with use_spatial_transformer, legacy=False, no class conditioning)
+# --------------------------------------------------------------------------------------------------------------------
+class TimeResBlock(nn.Module):
+    """openaimodel.py:178-289 (no up/down, no scale-shift): keys in_layers.{0,2}, emb_layers.1, out_layers.{0,3},
+    skip_connection."""
+
+    def __init__(self, cin: int, cout: int, emb: int, groups: int):
+        super().__init__()
+        self.in_layers = Slots({0: nn.GroupNorm(groups, cin), 2: nn.Conv2d(cin, cout, 3, padding=1)})
+        self.emb_layers = Slots({1: nn.Linear(emb, cout)})
+        self.out_layers = Slots({0: nn.GroupNorm(groups, cout), 3: nn.Conv2d(cout, cout, 3, padding=1)})
+        self.skip_connection = nn.Identity() if cin == cout else nn.Conv2d(cin, cout, 1)
+
+    def forward(self, x: torch.Tensor, act_emb: torch.Tensor) -> torch.Tensor:
+        """``act_emb`` = SiLU(time embedding), computed once per network evaluation by the caller."""
+        h = self.in_layers[2](F.silu(self.in_layers[0](x)))
+        h = h + self.emb_layers[1](act_emb)[:, :, None, None]
+        h = self.out_layers[3](F.silu(self.out_layers[0](h)))
+        return self.skip_connection(x) + h
+
+
+class Attention(nn.Module):
+    """attention.py:152-196 — keys to_q, to_k, to_v (no bias), to_out.0."""
+
+    def __init__(self, dim: int, ctx_dim: int, heads: int):
+        super().__init__()
+        self.heads = heads
+        self.to_q = nn.Linear(dim, dim, bias=False)
+        self.to_k = nn.Linear(ctx_dim, dim, bias=False)
+        self.to_v = nn.Linear(ctx_dim, dim, bias=False)
+        self.to_out = Slots({0: nn.Linear(dim, dim)})
+
+    def forward(self, x: torch.Tensor, context: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, N, C = x.shape
+        if context is not None and context.shape[1] == 1:
+            # one context token: softmax over a single key is exactly 1, so every query returns v (Zero123's
+            # c_crossattn is [2B,1,768], guidance :285-287)
+            return self.to_out[0](self.to_v(context)).expand(B, N, C)
+        src = x if context is None else context
+        h = self.heads
+        q = self.to_q(x).view(B, N, h, C // h).transpose(1, 2)
+        k = self.to_k(src).view(B, src.shape[1], h, C // h).transpose(1, 2)
+        v = self.to_v(src).view(B, src.shape[1], h, C // h).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v)
+        return self.to_out[0](o.transpose(1, 2).reshape(B, N, C))
+
+
+class GatedFeedForward(nn.Module):
+    """attention.py:37-65 with glu=True — keys net.0.proj, net.2."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        proj = nn.Module()
+        proj.proj = nn.Linear(dim, dim * 8)
+        self.net = Slots({0: proj, 2: nn.Linear(dim * 4, dim)})
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        a, gate = self.net[0].proj(x).chunk(2, dim=-1)
+        return self.net[2](a * F.gelu(gate))
+
+
+class TransformerBlock(nn.Module):
+    """attention.py:199-246 — keys attn1, ff, attn2, norm1..3."""
+
+    def __init__(self, dim: int, heads: int, ctx_dim: int):
+        super().__init__()
+        self.attn1 = Attention(dim, dim, heads)
+        self.ff = GatedFeedForward(dim)
+        self.attn2 = Attention(dim, ctx_dim, heads)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+        x = x + self.attn1(self.norm1(x))
+        x = x + self.attn2(self.norm2(x), context)
+        return x + self.ff(self.norm3(x))
+
+
+class SpatialTransformer(nn.Module):
+    """attention.py:249-301 (depth 1) — keys norm (eps 1e-6), proj_in, transformer_blocks.0, proj_out."""
+
+    def __init__(self, ch: int, heads: int, ctx_dim: int, groups: int):
+        super().__init__()
+        self.norm = nn.GroupNorm(groups, ch, eps=1e-6)
+        self.proj_in = nn.Conv2d(ch, ch, 1)
+        self.transformer_blocks = nn.ModuleList([TransformerBlock(ch, heads, ctx_dim)])
+        self.proj_out = nn.Conv2d(ch, ch, 1)
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+        B, C, H, W = x.shape
+        h = _nhwc(self.norm(x).contiguous(memory_format=torch.channels_last))       # [B,H,W,C] view, no copy
+        t = _pointwise(self.proj_in, h).reshape(B, H * W, C)
+        for blk in self.transformer_blocks:
+            t = blk(t, context)
+        out = _pointwise(self.proj_out, t.view(B, H, W, C))
+        return _nchw(out) + x
+
+
+class ConvDown(nn.Module):
+    """openaimodel.py:144-175 with use_conv — key op."""
+
+    def __init__(self, ch: int):
+        super().__init__()
+        self.op = nn.Conv2d(ch, ch, 3, stride=2, padding=1)
+
+    def forward(self, x):
+        return self.op(x)
+
+
+class ConvUp(nn.Module):
+    """openaimodel.py:95-125 with use_conv — key conv."""
+
+    def __init__(self, ch: int):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+class Stage(nn.Module):
+    """One entry of input_blocks / output_blocks / the middle block: children named 0, 1, 2 as in the reference's
+    TimestepEmbedSequential (openaimodel.py:78-92)."""
+
+    def __init__(self, layers: Sequence[nn.Module]):
+        super().__init__()
+        for i, m in enumerate(layers):
+            self.add_module(str(i), m)
+
+    def forward(self, x, act_emb, context):
+        for m in self._modules.values():
+            if isinstance(m, TimeResBlock):
+                x = m(x, act_emb)
+            elif isinstance(m, SpatialTransformer):
+                x = m(x, context)
+            else:
+                x = m(x)
+        return x
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    """.../diffusionmodules/util.py:174-199: [cos | sin] of t * max_period^(-i/half)."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    args = t[:, None].float() * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = F.pad(emb, (0, 1))
+    return emb
+
+
+class Zero123UNet(nn.Module):
+    def __init__(self, cfg: UNetConfig = UNetConfig()):
+        super().__init__()
+        self.cfg = cfg
+        mc, g = cfg.model_channels, cfg.groups
+        emb = mc * 4
+        self.time_embed = Slots({0: nn.Linear(mc, emb), 2: nn.Linear(emb, emb)})
+        attn = lambda ch: SpatialTransformer(ch, cfg.num_heads, cfg.context_dim, g)
+
+        stages: List[nn.Module] = [Stage([nn.Conv2d(cfg.in_channels, mc, 3, padding=1)])]
+        skips, ch, ds = [mc], mc, 1
+        for level, mult in enumerate(cfg.channel_mult):
+            for _ in range(cfg.num_res_blocks):
+                layers: List[nn.Module] = [TimeResBlock(ch, mult * mc, emb, g)]
+                ch = mult * mc
+                if ds in cfg.attention_resolutions:
+                    layers.append(attn(ch))
+                stages.append(Stage(layers))
+                skips.append(ch)
+            if level != len(cfg.channel_mult) - 1:
+                stages.append(Stage([ConvDown(ch)]))
+                skips.append(ch)
+                ds *= 2
+        self.input_blocks = nn.ModuleList(stages)
+        self.middle_block = Stage([TimeResBlock(ch, ch, emb, g), attn(ch), TimeResBlock(ch, ch, emb, g)])
+        ups: List[nn.Module] = []
+        for level, mult in reversed(list(enumerate(cfg.channel_mult))):
+            for i in range(cfg.num_res_blocks + 1):
+                layers = [TimeResBlock(ch + skips.pop(), mult * mc, emb, g)]
+                ch = mult * mc
+                if ds in cfg.attention_resolutions:
+                    layers.append(attn(ch))
+                if level and i == cfg.num_res_blocks:
+                    layers.append(ConvUp(ch))
+                    ds //= 2
+                ups.append(Stage(layers))
+        self.output_blocks = nn.ModuleList(ups)
+        self.out = Slots({0: nn.GroupNorm(g, ch), 2: nn.Conv2d(mc, cfg.out_channels, 3, padding=1)})
+
+    def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+        """x [N,in_channels,h,w], timesteps [N], context [N,L,context_dim] -> [N,out_channels,h,w] (openaimodel.py:810-842)."""
+        dt = self.time_embed[0].weight.dtype
+        e = timestep_embedding(timesteps, self.cfg.model_channels).to(dt)
+        act_emb = F.silu(self.time_embed[2](F.silu(self.time_embed[0](e))))
+        context = context.to(dt)
+        h = x.to(dt).contiguous(memory_format=torch.channels_last)
+        hs = []
+        for st in self.input_blocks:
+            h = st(h, act_emb, context)
+            hs.append(h)
+        h = self.middle_block(h, act_emb, context)
+        for st in self.output_blocks:
+            h = st(torch.cat([h, hs.pop()], dim=1), act_emb, context)
+        h = h.to(x.dtype)
+        return self.out[2](F.silu(self.out[0](h)))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# first-stage encoder (diffusionmodules/model.py:380-495; AutoencoderKL.encode, models/autoencoder.py:382-386)
+# --------------------------------------------------------------------------------------------------------------------
+class VAEResBlock(nn.Module):
+    """model.py:81-138 without the time embedding — keys norm1, conv1, norm2, conv2, nin_shortcut."""
+
+    def __init__(self, cin: int, cout: int, groups: int):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=1e-6)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=1e-6)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        if cin != cout:
+            self.nin_shortcut = nn.Conv2d(cin, cout, 1)
+
+    def forward(self, x):
+        h = self.conv1(F.silu(self.norm1(x)))
+        h = self.conv2(F.silu(self.norm2(h)))
+        return (self.nin_shortcut(x) if hasattr(self, "nin_shortcut") else x) + h
+
+
+class VAEAttention(nn.Module):
+    """model.py:148-191: single-head attention over the pixels — keys norm, q, k, v, proj_out (1x1 convolutions)."""
+
+    def __init__(self, ch: int, groups: int):
+        super().__init__()
+        self.norm = nn.GroupNorm(groups, ch, eps=1e-6)
+        self.q, self.k, self.v, self.proj_out = (nn.Conv2d(ch, ch, 1) for _ in range(4))
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        h = _nhwc(self.norm(x).contiguous(memory_format=torch.channels_last))
+        q, k, v = (_pointwise(m, h).reshape(B, 1, H * W, C) for m in (self.q, self.k, self.v))
+        o = F.scaled_dot_product_attention(q, k, v)                     # scale C^-0.5 = the reference's int(c)**-0.5
+        return x + _nchw(_pointwise(self.proj_out, o.reshape(B, H, W, C)))
+
+
+class VAEDownsample(nn.Module):
+    """model.py:61-78: zero-pad right/bottom by one, 3x3 stride-2 convolution — key conv."""
+
+    def __init__(self, ch: int):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, stride=2, padding=0)
+
+    def forward(self, x):
+        return self.conv(F.pad(x, (0, 1, 0, 1)))
+
+
+class Zero123Encoder(nn.Module):
+    def __init__(self, cfg: EncoderConfig = EncoderConfig()):
+        super().__init__()
+        self.cfg = cfg
+        g = cfg.groups
+        self.conv_in = nn.Conv2d(cfg.in_channels, cfg.ch, 3, padding=1)
+        self.down = nn.ModuleList()
+        cin = cfg.ch
+        for lvl, mult in enumerate(cfg.ch_mult):
+            level = nn.Module()
+            level.block = nn.ModuleList()
+            level.attn = nn.ModuleList()          # attn_resolutions: [] in the YAML; kept for key compatibility
+            for _ in range(cfg.num_res_blocks):
+                level.block.append(VAEResBlock(cin, cfg.ch * mult, g))
+                cin = cfg.ch * mult
+            if lvl != len(cfg.ch_mult) - 1:
+                level.downsample = VAEDownsample(cin)
+            self.down.append(level)
+        self.mid = nn.Module()
+        self.mid.block_1 = VAEResBlock(cin, cin, g)
+        self.mid.attn_1 = VAEAttention(cin, g)
+        self.mid.block_2 = VAEResBlock(cin, cin, g)
+        self.norm_out = nn.GroupNorm(g, cin, eps=1e-6)
+        self.conv_out = nn.Conv2d(cin, 2 * cfg.z_channels, 3, padding=1)
+
+    def forward(self, x):
+        h = self.conv_in(x.contiguous(memory_format=torch.channels_last))
+        for level in self.down:
+            for blk in level.block:
+                h = blk(h)
+            if hasattr(level, "downsample"):
+                h = level.downsample(h)
+        h = self.mid.block_2(self.mid.attn_1(self.mid.block_1(h)))
+        return self.conv_out(F.silu(self.norm_out(h)))
+
+
+class DiagonalGaussian:
+    """modules/distributions/distributions.py:24-37,68-69: moments -> (mean, clamped logvar); sample / mode."""
+
+    def __init__(self, moments: torch.Tensor):
+        self.mean, logvar = moments.chunk(2, dim=1)
+        self.logvar = logvar.clamp(-30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+
+    def sample(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """The reference draws the noise on the HOST generator and moves it (``torch.randn(shape).to(device)``,
+        distributions.py:38-42); here it is drawn on the tensor's device (no per-step H2D copy, CUDA-graph
+        capturable) unless a CPU ``generator`` is handed in."""
+        if generator is not None and generator.device.type == "cpu" and self.mean.device.type != "cpu":
+            eps = torch.randn(self.mean.shape, generator=generator).to(self.mean.device)
+        else:
+            eps = torch.randn(self.mean.shape, generator=generator, device=self.mean.device)
+        return self.mean + self.std * eps        # fp32 noise: half-precision moments promote to fp32, as in the reference
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+
+class _FirstStage(nn.Module):
+    def __init__(self, cfg: EncoderConfig):
+        super().__init__()
+        self.encoder = Zero123Encoder(cfg)
+        self.quant_conv = nn.Conv2d(2 * cfg.z_channels, 2 * cfg.embed_dim, 1)
+
+
+class _Wrapper(nn.Module):
+    def __init__(self, cfg: UNetConfig):
+        super().__init__()
+        self.diffusion_model = Zero123UNet(cfg)
+
+
+class Zero123Model(nn.Module):
+    """The slice of ``LatentDiffusion`` the guidance calls per step; parameter prefixes ``model.diffusion_model.``,
+    ``first_stage_model.{encoder,quant_conv}.`` and ``cc_projection.`` as in the Zero123 checkpoint (the decoder is
+    dropped by ``vram_O``, guidance :66-68; the CLIP image encoder only runs once at set-up, :179-222, and is
+    represented here by its cached outputs ``c_crossattn`` / ``c_concat`` held by the guidance)."""
+
+    def __init__(self, cfg: Zero123Config = Zero123Config()):
+        super().__init__()
+        self.cfg = cfg
+        self.model = _Wrapper(cfg.unet)
+        self.first_stage_model = _FirstStage(cfg.encoder)
+        self.cc_projection = nn.Linear(cfg.cc_in, cfg.cc_out)
+        with torch.no_grad():                                   # ddpm.py:653-655
+            self.cc_projection.weight.zero_()
+            self.cc_projection.weight[:, :cfg.cc_out].copy_(torch.eye(cfg.cc_out))
+            self.cc_projection.bias.zero_()
+        self.scale_factor = cfg.scale_factor
+
+    def encode_first_stage(self, x: torch.Tensor) -> DiagonalGaussian:
+        fs = self.first_stage_model
+        return DiagonalGaussian(fs.quant_conv(fs.encoder(x)))
+
+    def get_first_stage_encoding(self, posterior, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """ddpm.py:766-775: scale_factor * posterior.sample()."""
+        z = posterior.sample(generator) if isinstance(posterior, DiagonalGaussian) else posterior
+        return self.scale_factor * z
+
+    def apply_model(self, x_noisy: torch.Tensor, t: torch.Tensor, cond: Dict[str, List[torch.Tensor]]) -> torch.Tensor:
+        """ddpm.py:1130 + DiffusionWrapper 'hybrid' (:1953-1956)."""
+        xc = torch.cat([x_noisy] + list(cond["c_concat"]), dim=1)
+        cc = torch.cat(list(cond["c_crossattn"]), dim=1)
+        return self.model.diffusion_model(xc, t, cc)
+
+
+def unet_flops(cfg: UNetConfig, n: int, h: int, w: int, ctx_len: int = 1) -> float:
+    """Multiply-add FLOPs (2 per MAC) of one UNet evaluation as EXECUTED here (single-token cross-attention shortcut
+    included) on a batch of ``n`` latents of ``h x w``.  Walks the same block plan as the constructor."""
+    mc, emb = cfg.model_channels, cfg.model_channels * 4
+    fl = 2.0 * n * (mc * emb + emb * emb)
+    conv = lambda cin, cout, hh, ww, k=3: 2.0 * n * cin * cout * k * k * hh * ww
+
+    def res(cin, cout, hh, ww):
+        f = conv(cin, cout, hh, ww) + conv(cout, cout, hh, ww) + 2.0 * n * emb * cout
+        return f + (conv(cin, cout, hh, ww, 1) if cin != cout else 0.0)
+
+    def attn(ch, hh, ww):
+        t = hh * ww
+        f = 2 * conv(ch, ch, hh, ww, 1)                                  # proj_in / proj_out
+        f += 2.0 * n * t * ch * ch * 4 + 4.0 * n * t * t * ch            # self-attention: q,k,v,out + QK^T, PV
+        if ctx_len == 1:
+            f += 2.0 * n * (cfg.context_dim * ch + ch * ch)              # to_v + to_out on one token
+        else:
+            f += 2.0 * n * (t * ch * ch * 2 + ctx_len * cfg.context_dim * ch * 2) + 4.0 * n * t * ctx_len * ch
+        return f + 2.0 * n * t * (ch * 8 * ch + 4 * ch * ch)             # GEGLU feed-forward
+
+    fl += conv(cfg.in_channels, mc, h, w)
+    skips, ch, ds, hh, ww = [mc], mc, 1, h, w
+    for level, mult in enumerate(cfg.channel_mult):
+        for _ in range(cfg.num_res_blocks):
+            fl += res(ch, mult * mc, hh, ww)
+            ch = mult * mc
+            if ds in cfg.attention_resolutions:
+                fl += attn(ch, hh, ww)
+            skips.append(ch)
+        if level != len(cfg.channel_mult) - 1:
+            hh, ww = hh // 2, ww // 2
+            fl += conv(ch, ch, hh, ww)
+            skips.append(ch)
+            ds *= 2
+    fl += 2 * res(ch, ch, hh, ww) + attn(ch, hh, ww)
+    for level, mult in reversed(list(enumerate(cfg.channel_mult))):
+        for i in range(cfg.num_res_blocks + 1):
+            fl += res(ch + skips.pop(), mult * mc, hh, ww)
+            ch = mult * mc
+            if ds in cfg.attention_resolutions:
+                fl += attn(ch, hh, ww)
+            if level and i == cfg.num_res_blocks:
+                hh, ww = hh * 2, ww * 2
+                fl += conv(ch, ch, hh, ww)
+                ds //= 2
+    return fl + conv(mc, cfg.out_channels, hh, ww)
+
+
+def encoder_flops(cfg: EncoderConfig, n: int, h: int, w: int) -> float:
+    """Forward FLOPs of the first-stage encoder (+ quant_conv) on ``n`` images of ``h x w``."""
+    conv = lambda cin, cout, hh, ww, k=3: 2.0 * n * cin * cout * k * k * hh * ww
+    fl = conv(cfg.in_channels, cfg.ch, h, w)
+    cin, hh, ww = cfg.ch, h, w
+    for lvl, mult in enumerate(cfg.ch_mult):
+        for _ in range(cfg.num_res_blocks):
+            cout = cfg.ch * mult
+            fl += conv(cin, cout, hh, ww) + conv(cout, cout, hh, ww) + (conv(cin, cout, hh, ww, 1) if cin != cout else 0.0)
+            cin = cout
+        if lvl != len(cfg.ch_mult) - 1:
+            hh, ww = hh // 2, ww // 2
+            fl += conv(cin, cin, hh, ww)
+    t = hh * ww
+    fl += 4 * conv(cin, cin, hh, ww) + 4 * conv(cin, cin, hh, ww, 1) + 4.0 * n * t * t * cin
+    return fl + conv(cin, 2 * cfg.z_channels, hh, ww) + conv(2 * cfg.z_channels, 2 * cfg.embed_dim, hh, ww, 1)

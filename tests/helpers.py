@@ -67,3 +67,58 @@ def matrix_to_quaternion(R: torch.Tensor) -> torch.Tensor:
     cand = cand / (2.0 * q_abs[..., None].clamp_min(0.1))
     best = q_abs.argmax(dim=-1)
     return cand[torch.arange(R.shape[0]), best]
+
+
+def seeded_fill(module: torch.nn.Module, seed: int) -> None:
+    """Deterministic parameter fill in state_dict order: matrices/filters ~ N(0, 0.5/sqrt(fan_in)), norm scales
+    ~ 1 + N(0, 0.2), biases ~ N(0, 0.2).  Used by tests/golden/make_zero123_golden.py on the reference's modules and by
+    the tests on the product's: equal names, order and shapes give equal weights."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.state_dict().items():
+            if not p.dtype.is_floating_point:
+                continue
+            r = torch.randn(p.shape, generator=g)
+            if p.dim() > 1:
+                p.copy_(r * (0.5 / math.sqrt(p[0].numel())))
+            elif name.endswith("weight"):
+                p.copy_(1.0 + 0.2 * r)
+            else:
+                p.copy_(0.2 * r)
+
+
+class SDSStubModel(torch.nn.Module):
+    """Small seeded stand-in for the latent-diffusion network behind the SDS step (tests/golden/make_sds_golden.py and
+    tests/test_sds.py build the SAME stub): ``moments`` plays the first-stage encoder + quant_conv (8x downsampling to 2x4
+    moment channels), ``apply_model`` the hybrid-conditioned denoiser.  What it computes is irrelevant; that both
+    sides compute the same thing is what lets the SDS arithmetic be compared."""
+
+    scale_factor = 0.18215
+
+    def __init__(self, seed: int = 3):
+        super().__init__()
+        self.enc = torch.nn.Conv2d(3, 8, 8, stride=8)
+        self.cc_projection = torch.nn.Linear(772, 768)
+        self.den = torch.nn.Conv2d(8, 4, 3, padding=1)
+        self.den_t = torch.nn.Conv2d(8, 4, 1)
+        self.ctx = torch.nn.Linear(768, 4)
+        seeded_fill(self, seed)
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    def moments(self, x):
+        return self.enc(x)
+
+    def apply_model(self, x, t, cond):
+        xc = torch.cat([x] + list(cond["c_concat"]), dim=1)
+        cc = torch.cat(list(cond["c_crossattn"]), dim=1)
+        phase = torch.sin(t.float() / 1000.0 * 3.0).reshape(-1, 1, 1, 1)
+        return self.den(xc) + phase * self.den_t(xc) + self.ctx(cc).mean(dim=1).reshape(-1, 4, 1, 1)
+
+
+def sds_stub_inputs(seed: int, B: int = 3, n_frames: int = 5, hw: int = 48):
+    g = torch.Generator().manual_seed(seed)
+    return {"rgb": torch.rand(B, hw, hw, 3, generator=g),
+            "elevation": torch.rand(B, generator=g) * 90 - 10, "azimuth": torch.rand(B, generator=g) * 360 - 180,
+            "camera_distances": torch.full((B,), 3.8), "frame_indices": torch.randint(0, n_frames, (B,), generator=g),
+            "c_crossattn": torch.randn(n_frames, 1, 768, generator=g), "c_concat": torch.randn(n_frames, 4, 32, 32, generator=g)}
