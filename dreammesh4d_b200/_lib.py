@@ -72,6 +72,7 @@ SIGNATURES = {
     "dm4d_raster_plan": (ctypes.c_int, [POINTER(RasterDesc), c_void_p, POINTER(c_int64), c_void_p]),
     "dm4d_raster_render": (ctypes.c_int, [POINTER(RasterDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
     "dm4d_raster_forward": (ctypes.c_int, [POINTER(RasterDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dm4d_raster_render_features": (ctypes.c_int, [POINTER(RasterDesc), POINTER(RasterDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
     "dm4d_raster_status": (ctypes.c_int, [POINTER(RasterDesc), POINTER(c_int64), POINTER(c_int32), c_void_p]),
     "dm4d_raster_backward": (ctypes.c_int, [POINTER(RasterDesc)] + [c_void_p] * 12),
     "dm4d_raster_export_state": (ctypes.c_int, [POINTER(RasterDesc), c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -16,7 +16,7 @@ void dm4d_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* dm4d_last_error(void) { return g_err; }
-extern "C" int dm4d_version(void) { return 110; }   // 1.1: + postops, hexplane, graph_knn
+extern "C" int dm4d_version(void) { return 120; }   // 1.2: + raster_render_features (plan reuse), status header
 
 void raster_sizes(int P, int H, int W, int n_views, int channels, long long capacity, uint64_t* geom, uint64_t* bin,
                   uint64_t* img, uint64_t* bwd) {
@@ -125,6 +125,24 @@ extern "C" int dm4d_raster_forward(const dm4d_raster_desc* d, float* out_color, 
     int rc = dm4d_raster_plan(d, radii, nullptr, stream);
     if (rc) return rc;
     return dm4d_raster_render(d, out_color, out_depth, out_alpha, stream);
+}
+
+extern "C" int dm4d_raster_render_features(const dm4d_raster_desc* planned, const dm4d_raster_desc* d, float* out_color,
+                                           float* out_depth, float* out_alpha, void* stream) {
+    RasterLayout Ls, Ld;
+    int rc = raster_make_layout(planned, &Ls);
+    if (rc) return rc;
+    if ((rc = raster_make_layout(d, &Ld))) return rc;
+    if (!out_color || !out_depth || !out_alpha) { dm4d_set_error("NULL output pointer"); return DM4D_EINVAL; }
+    if (d->P != planned->P || d->H != planned->H || d->W != planned->W || d->n_views != planned->n_views ||
+        d->channels != planned->channels || d->bin_capacity != planned->bin_capacity || d->geom != planned->geom ||
+        d->bin == planned->bin || d->img == planned->img) {
+        dm4d_set_error("dm4d_raster_render_features: desc must share sizes and `geom` with the planned desc and bring its own bin / img");
+        return DM4D_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = launch_rebind_features(d, Ls, Ld, s))) return rc;
+    return launch_render_forward(d, Ld, out_color, out_depth, out_alpha, s);
 }
 
 extern "C" int dm4d_raster_status(const dm4d_raster_desc* d, int64_t* num_rendered_host, int32_t* overflow_host,

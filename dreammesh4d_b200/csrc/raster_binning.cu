@@ -484,6 +484,70 @@ int launch_scatter_sort_pack(const RasterLayout& L, cudaStream_t s) {
     return DM4D_OK;
 }
 
+// ---- feature re-binding (second rasterizer call of a view: same geometry, other per-Gaussian features) ----------------
+namespace {
+struct RebindArgs {
+    int P, rec, channels, n_sets;
+    const float* colors;  long long colors_stride;
+    const float* colors2; long long colors2_stride;
+    const float* view_params;
+    const unsigned int* view_first;   // tile_offset of the source plan: view v owns instances [view_first[v*tiles], view_first[(v+1)*tiles])
+    int n_views, tiles;
+};
+// One thread per sorted instance: copy the geometric half of the record (position, conic, opacity, cell mask, id, depth)
+// and gather the new features by Gaussian id.  Reads 48/64 B + 12/24 B, writes 48/64 B per instance.
+__global__ void __launch_bounds__(256) rebind_features_kernel(RebindArgs a, const BinHeader* __restrict__ hdr,
+                                                              const float4* __restrict__ src, float4* __restrict__ dst) {
+    const unsigned long long total = hdr->overflow ? 0ull : hdr->total;
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int r4 = a.rec / 4;
+    const float4 r0 = src[i * r4 + 0], r1 = src[i * r4 + 1];
+    const int id = __float_as_int(r1.w);
+    // view of this instance: binary search over the per-view first offsets (n_views is small)
+    int v = 0;
+    {
+        int lo = 0, hi = a.n_views - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((unsigned long long)a.view_first[(size_t)mid * a.tiles] <= i) lo = mid; else hi = mid - 1;
+        }
+        v = lo;
+    }
+    const float* vp = a.view_params + (size_t)v * DM4D_VIEW_STRIDE;
+    const long long set = min(max((long long)vp[DM4D_VIEW_SET], 0ll), (long long)a.n_sets - 1);
+    const float* c0 = a.colors + set * a.colors_stride + (size_t)id * 3;
+    dst[i * r4 + 0] = r0;
+    dst[i * r4 + 1] = r1;
+    if (a.channels <= 3) {
+        const float depth = src[i * r4 + 2].w;
+        dst[i * r4 + 2] = make_float4(c0[0], c0[1], c0[2], depth);
+    } else {
+        const float depth = src[i * r4 + 3].z;
+        const float* c1 = a.colors2 + set * a.colors2_stride + (size_t)id * 3;
+        dst[i * r4 + 2] = make_float4(c0[0], c0[1], c0[2], c1[0]);
+        dst[i * r4 + 3] = make_float4(c1[1], c1[2], depth, 0.f);
+    }
+}
+}  // namespace
+
+int launch_rebind_features(const dm4d_raster_desc* d, const RasterLayout& src, const RasterLayout& dst, cudaStream_t s) {
+    // header + tile tables (count, offset, cursor, order) are contiguous at the start of the bin workspace
+    const size_t head = (size_t)((const char*)src.keys - (const char*)src.hdr);
+    DM4D_CUDA_CHECK(cudaMemcpyAsync(dst.hdr, src.hdr, head, cudaMemcpyDeviceToDevice, s));
+    if (src.capacity == 0) return DM4D_OK;
+    RebindArgs a;
+    a.P = src.P; a.rec = src.rec; a.channels = src.channels; a.n_sets = d->n_sets;
+    a.colors = d->colors; a.colors_stride = d->colors_stride;
+    a.colors2 = d->colors2; a.colors2_stride = d->colors2_stride;
+    a.view_params = d->view_params; a.view_first = src.tile_offset; a.n_views = src.n_views; a.tiles = src.tiles;
+    const unsigned blocks = (unsigned)((src.capacity + 255) / 256);
+    rebind_features_kernel<<<blocks, 256, 0, s>>>(a, src.hdr, reinterpret_cast<const float4*>(src.stream),
+                                                  reinterpret_cast<float4*>(dst.stream));
+    DM4D_CUDA_CHECK(cudaGetLastError());
+    return DM4D_OK;
+}
+
 int launch_export_state(const RasterLayout& L, int view, unsigned int* ranges, unsigned int* point_list,
                         long long cap, unsigned int* n_contrib, cudaStream_t s) {
     long long n = L.tiles;

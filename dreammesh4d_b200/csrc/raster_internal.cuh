@@ -82,6 +82,7 @@ int launch_render_forward(const dm4d_raster_desc* d, const RasterLayout& L, floa
                           float* out_alpha, cudaStream_t s);
 int launch_render_backward(const dm4d_raster_desc* d, const RasterLayout& L, const float* out_alpha,
                            const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, cudaStream_t s);
+int launch_rebind_features(const dm4d_raster_desc* d, const RasterLayout& src, const RasterLayout& dst, cudaStream_t s);
 int launch_export_state(const RasterLayout& L, int view, unsigned int* ranges, unsigned int* point_list,
                         long long cap, unsigned int* n_contrib, cudaStream_t s);
 

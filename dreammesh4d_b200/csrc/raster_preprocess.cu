@@ -11,7 +11,7 @@
 namespace {
 
 struct PreArgs {
-    int P, H, W, n_views, channels, gx, gy, tiles, rec, acc;
+    int P, H, W, n_views, n_sets, channels, gx, gy, tiles, rec, acc;
     const float* means3D;   long long means3D_stride;
     const float* scales;    long long scales_stride;
     const float* rotations; long long rotations_stride;
@@ -105,7 +105,7 @@ __device__ __forceinline__ unsigned int preprocess_one(const PreArgs& a, long lo
     const int v = (int)(idx / a.P);
     const int g = (int)(idx - (long long)v * a.P);
     const float* __restrict__ vp = a.view_params + (size_t)v * DM4D_VIEW_STRIDE;
-    const long long set = (long long)vp[DM4D_VIEW_SET];
+    const long long set = min(max((long long)vp[DM4D_VIEW_SET], 0ll), (long long)a.n_sets - 1);   // never index outside the sets
 
     a.radii[idx] = 0;
     a.g_rect[idx] = 0u;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK) preprocess_backward_kernel(PreBwdA
     const int v = (int)(idx / a.P);
     const int g = (int)(idx - (long long)v * a.P);
     const float* __restrict__ vp = a.view_params + (size_t)v * DM4D_VIEW_STRIDE;
-    const long long set = (long long)vp[DM4D_VIEW_SET];
+    const long long set = min(max((long long)vp[DM4D_VIEW_SET], 0ll), (long long)a.n_sets - 1);
     const bool live = a.g_rect[idx] != 0u;
     const float* acc = b.accum + (size_t)idx * a.acc;
 
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK) preprocess_backward_kernel(PreBwdA
 
 PreArgs make_args(const dm4d_raster_desc* d, const RasterLayout& L, int32_t* radii) {
     PreArgs a;
-    a.P = L.P; a.H = L.H; a.W = L.W; a.n_views = L.n_views; a.channels = L.channels;
+    a.P = L.P; a.H = L.H; a.W = L.W; a.n_views = L.n_views; a.n_sets = d->n_sets; a.channels = L.channels;
     a.gx = L.gx; a.gy = L.gy; a.tiles = L.tiles; a.rec = L.rec; a.acc = L.acc;
     a.means3D = d->means3D; a.means3D_stride = d->means3D_stride;
     a.scales = d->scales; a.scales_stride = d->scales_stride;

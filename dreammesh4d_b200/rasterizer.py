@@ -11,6 +11,9 @@ autograd plumbing only; all arithmetic runs in libdm4d.so.
 from __future__ import annotations
 
 import ctypes
+import os
+import warnings
+import weakref
 from typing import NamedTuple, Optional
 
 import torch
@@ -61,6 +64,8 @@ def _prep(t: torch.Tensor, k: int, name: str):
             raise ValueError(f"{name} must be [P,{k}] or [S,P,{k}], got {tuple(t.shape)}")
         return t, 0, 1
     if t.dim() == 3 and t.shape[2] == k:
+        if t.shape[0] == 1:          # a single set is shared by every view: stride 0, gradients summed over views
+            return t, 0, 1
         return t, t.shape[1] * k, t.shape[0]
     raise ValueError(f"{name} must be [P,{k}] or [S,P,{k}], got {tuple(t.shape)}")
 
@@ -87,6 +92,10 @@ class RasterState:
 
     def __init__(self, desc: RasterDesc, keep: list, capacity: int):
         self.desc, self.keep, self.capacity = desc, keep, capacity
+        self.radii: Optional[torch.Tensor] = None
+        self.alpha_version = 0
+        self.pending = None          # deferred overflow verification of a speculative capacity (CapacityBook)
+        self.overflowed = False
 
     def status(self) -> tuple[int, bool]:
         """(num_rendered, overflow) — synchronises the current stream."""
@@ -95,6 +104,16 @@ class RasterState:
         check(_lib.lib().dm4d_raster_status(ctypes.byref(self.desc), ctypes.byref(n), ctypes.byref(o),
                                             torch.cuda.current_stream().cuda_stream), "dm4d_raster_status")
         return int(n.value), bool(o.value)
+
+    def overflow_flag(self) -> torch.Tensor:
+        """Device-side int32 view of the overflow flag of this batch (no synchronisation; CUDA-graph capturable).
+        The bin workspace starts with the status header {uint64 num_rendered; uint32 overflow; uint32 pad}
+        (include/dm4d.h, "status header")."""
+        return self.keep[8][8:12].view(torch.int32)
+
+    def num_rendered_tensor(self) -> torch.Tensor:
+        """Device-side int64 view of the instance count R of this batch (no synchronisation)."""
+        return self.keep[8][0:8].view(torch.int64)
 
     def export_view(self, view: int):
         """Integer binning state of one view (ranges [T,2], point_list [R_v], n_contrib [H,W])."""
@@ -113,7 +132,7 @@ class RasterState:
 class _RasterizeBatch(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, opacities, scales, rotations, colors, colors2, view_params, H, W,
-                capacity, distinct_sets, state_out, workspace):
+                capacity, distinct_sets, state_out, workspace, plan=None):
         l = _lib.lib()
         dev = means3D.device
         if dev.type != "cuda":
@@ -158,12 +177,26 @@ class _RasterizeBatch(torch.autograd.Function):
 
         u8 = dict(dtype=torch.uint8, device=dev)
         scratch = (lambda name, n: torch.empty(n, **u8)) if workspace is None else (lambda name, n: workspace.get(name, n, dev))
-        radii = torch.empty(B, P, dtype=torch.int32, device=dev)
+        radii = None if plan is not None else torch.empty(B, P, dtype=torch.int32, device=dev)
         color = torch.empty(B, channels, H, W, dtype=torch.float32, device=dev)
         depth = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
         alpha = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
 
-        if capacity is None:
+        if plan is not None:
+            # second pass over a planned batch (same geometry, other features): projection, binning and the depth
+            # sort of `plan` are re-used; only the features are re-bound onto the sorted stream (dm4d.h)
+            pd = plan.desc
+            if (pd.P, pd.H, pd.W, pd.n_views, pd.channels) != (P, int(H), int(W), B, channels):
+                raise ValueError("plan does not match this call (P, H, W, views or channels differ)")
+            capacity = plan.capacity
+            gb, bb, ib, wb = sizes(capacity)
+            geom, bin_, img = plan.keep[7], scratch("bin", bb), scratch("img", ib)
+            d.geom, d.geom_bytes, d.img, d.img_bytes = ptr(geom), gb, ptr(img), ib
+            d.bin, d.bin_bytes, d.bin_capacity = ptr(bin_), bb, capacity
+            check(l.dm4d_raster_render_features(ctypes.byref(pd), ctypes.byref(d), ptr(color), ptr(depth), ptr(alpha),
+                                                stream), "dm4d_raster_render_features")
+            radii = plan.radii.detach()          # same storage, fresh tensor object
+        elif capacity is None:
             # exact sizing with one host read-back of num_rendered, like the replaced rasterizer:
             # plan into a capacity-0 workspace to learn R, then run the forward at capacity R
             gb, bb, ib, wb = sizes(0)
@@ -188,6 +221,8 @@ class _RasterizeBatch(torch.autograd.Function):
                   "dm4d_raster_forward")
 
         state = RasterState(d, [m, sc, ro, op, co, c2, vp, geom, bin_, img, alpha], capacity)
+        state.radii = radii
+        state.alpha_version = alpha._version      # the backward reads T_final = 1 - alpha from this very tensor
         ctx.state = state
         ctx.workspace = workspace
         ctx.shapes = (means3D.shape, scales.shape, rotations.shape, opacities.shape, colors.shape,
@@ -202,8 +237,14 @@ class _RasterizeBatch(torch.autograd.Function):
     def backward(ctx, g_color, g_radii, g_depth, g_alpha):
         l = _lib.lib()
         st: RasterState = ctx.state
+        if st.pending is not None:
+            st.pending.resolve(st)               # the header copy finished long ago: no stall
         d = st.desc
         m, sc, ro, op, co, c2, vp, geom, bin_, img, alpha = st.keep
+        if alpha._version != st.alpha_version:
+            raise RuntimeError("the alpha image returned by the rasterizer was modified in place before backward(); the "
+                               "backward reads the final transmittance from it (as the replaced rasterizer does) — "
+                               "clone it before editing")
         dev = m.device
         stream = torch.cuda.current_stream().cuda_stream
         _, _, _, wb = (ctypes.c_uint64(0) for _ in range(4))
@@ -234,12 +275,12 @@ class _RasterizeBatch(torch.autograd.Function):
         rs = lambda t, s: None if t is None else t.reshape(s)
         return (rs(d_means3D, sh[0]), d_means2D, rs(d_opac, sh[3]), rs(d_scales, sh[1]), rs(d_rots, sh[2]),
                 rs(d_colors, sh[4]), None if d_colors2 is None else rs(d_colors2, sh[5]),
-                None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None)
 
 
 def rasterize_batch(means3D, opacities, scales, rotations, colors, view_params, H, W, colors2=None, means2D=None,
                     capacity: Optional[int] = None, distinct_sets: bool = False, state_out: Optional[list] = None,
-                    workspace: Optional[RasterWorkspace] = None):
+                    workspace: Optional[RasterWorkspace] = None, plan: Optional[RasterState] = None):
     """Rasterizes a batch of views in one launch sequence.
 
     Attributes are ``[P,k]`` (shared by all views) or ``[S,P,k]`` (one set per timestamp; each view picks
@@ -248,11 +289,13 @@ def rasterize_batch(means3D, opacities, scales, rotations, colors, view_params, 
     diff_sugar_rasterizer_temporal.py:108-113).  ``capacity=None`` sizes the binning workspace exactly
     with one host read-back (the replaced rasterizer's behaviour); an integer keeps the call fully
     asynchronous (check ``state.status()`` for overflow).  ``workspace``: optional persistent scratch
-    (``RasterWorkspace``) for strictly alternating forward/backward call sequences.
+    (``RasterWorkspace``) for strictly alternating forward/backward call sequences.  ``plan``: the ``RasterState`` of an
+    earlier call on the SAME means / scales / rotations / opacities / cameras — projection, binning and the depth sort
+    are re-used and only ``colors`` (/``colors2``) are re-bound (the renderer's normal pass, temporal.py:202-211).
     Returns ``color [B,C,H,W], radii [B,P] int32, depth [B,1,H,W], alpha [B,1,H,W]``.
     """
     return _RasterizeBatch.apply(means3D, means2D, opacities, scales, rotations, colors, colors2, view_params,
-                                 int(H), int(W), capacity, distinct_sets, state_out, workspace)
+                                 int(H), int(W), capacity, distinct_sets, state_out, workspace, plan)
 
 
 # --------------------------------------------------------------------------------------------
@@ -308,12 +351,134 @@ def sh_to_rgb(shs: torch.Tensor, means3D: torch.Tensor, campos: torch.Tensor, de
     return torch.clamp_min(res + 0.5, 0.0)
 
 
+class CapacityBook:
+    """Grow-only binning capacities for the per-view drop-in calls, replacing the replaced module's ``num_rendered``
+    read-back in the middle of every forward.
+
+    The first call of a (P, H, W, channels) shape is sized exactly (one read-back, as upstream does on every call);
+    later calls run fully asynchronously at ``margin x`` the largest instance count seen.  Every speculative call
+    queues a 16-byte copy of the device status header (include/dm4d.h) to pinned memory; it is read when it has
+    landed (next call / the call's own backward) to keep the high-water mark current.  If a call ever exceeded its
+    capacity — the instance count would have to jump by more than the margin between consecutive calls — that call
+    rendered background: a RuntimeWarning says so, its backward returns zero gradients, the capacity grows, and the
+    next call of the shape is sized exactly again.  ``exact = True`` (or DM4D_EXACT_SIZING=1) restores one read-back
+    per call."""
+
+    SLOTS = 256
+
+    def __init__(self, margin: float = 1.5, slack: int = 1 << 16):
+        self.margin, self.slack = margin, slack
+        self.exact = bool(int(os.environ.get("DM4D_EXACT_SIZING", "0")))
+        self.high: dict = {}             # shape key -> largest num_rendered seen
+        self.force_exact: set = set()
+        self._host = None
+        self._free: list = []
+        self._queue: list = []           # (event, slot, key, weakref(state))
+
+    def capacity(self, key) -> Optional[int]:
+        """None = size this call exactly (read-back)."""
+        self.poll()
+        if self.exact or key not in self.high or key in self.force_exact:
+            self.force_exact.discard(key)
+            return None
+        return int(self.high[key] * self.margin) + self.slack
+
+    def note_exact(self, key, n: int) -> None:
+        self.high[key] = max(self.high.get(key, 0), int(n))
+
+    def track(self, key, state: RasterState) -> None:
+        """Queues the asynchronous header read-back of a speculative call."""
+        if self._host is None:
+            self._host = torch.zeros(self.SLOTS, 2, dtype=torch.int64).pin_memory()
+            self._free = list(range(self.SLOTS))
+        if not self._free:
+            self.poll(block=True)
+        slot = self._free.pop()
+        self._host[slot].copy_(state.keep[8][0:16].view(torch.int64), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        ent = _Pending(self, ev, slot, key)
+        state.pending = ent
+        self._queue.append((ent, weakref.ref(state)))
+
+    def poll(self, block: bool = False) -> None:
+        keep = []
+        for ent, ref in self._queue:
+            if ent.done:
+                continue
+            if block or ent.event.query():
+                ent.resolve(ref())
+            else:
+                keep.append((ent, ref))
+        self._queue = keep
+
+
+class _Pending:
+    def __init__(self, book: CapacityBook, event, slot: int, key):
+        self.book, self.event, self.slot, self.key, self.done = book, event, slot, key, False
+
+    def resolve(self, state: Optional[RasterState]) -> None:
+        if self.done:
+            return
+        self.event.synchronize()
+        total, flags = (int(x) for x in self.book._host[self.slot])
+        self.book._free.append(self.slot)
+        self.done = True
+        self.book.note_exact(self.key, total)
+        if flags & 0xffffffff:
+            self.book.force_exact.add(self.key)
+            if state is not None:
+                state.overflowed = True
+            warnings.warn(f"dreammesh4d_b200 rasterizer: a drop-in call produced {total} instances, more than its "
+                          "speculative capacity; that call rendered background and its backward returns zero "
+                          "gradients. The capacity has been raised and the next call is sized exactly "
+                          "(set DM4D_EXACT_SIZING=1 to size every call exactly).", RuntimeWarning, stacklevel=3)
+        if state is not None:
+            state.pending = None
+
+
+CAPACITY_BOOK = CapacityBook()
+
+
 class GaussianRasterizer(nn.Module):
-    """Same constructor/forward signature and 4-tuple return as the replaced module."""
+    """Same constructor/forward signature and 4-tuple return as the replaced module.
+
+    Zero-edit fast path for the reference's renderer, which builds one rasterizer per view and calls it twice with the
+    same means3D / scales / rotations / opacities objects (RGB, then normals as colours; temporal.py:144,169-178,
+    202-211): the first call's plan (projection, binning, depth sort) is kept on the instance and the second call only
+    re-binds its colours (``dm4d_raster_render_features``).  A hit requires the SAME tensor objects at the same
+    ``_version`` — a freed-and-reallocated tensor can never alias a stale plan."""
 
     def __init__(self, raster_settings: GaussianRasterizationSettings):
         super().__init__()
         self.raster_settings = raster_settings
+        self._plan = None            # (RasterState, (weakref, version) x 4)
+        self._vp = None
+
+    def _view_params(self) -> torch.Tensor:
+        """[1,48] camera block, built once per instance with two small device ops."""
+        if self._vp is None:
+            rs = self.raster_settings
+            dev = rs.viewmatrix.device
+            tail = torch.tensor([float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier), 0.0, 0.0],
+                                dtype=torch.float32).to(dev, non_blocking=True)
+            bg = rs.bg.reshape(-1).to(device=dev, dtype=torch.float32)[:3]
+            pad = torch.zeros(DM4D_VIEW_STRIDE - 43, dtype=torch.float32, device=dev)
+            self._vp = torch.cat([rs.viewmatrix.reshape(16).float(), rs.projmatrix.reshape(16).float(),
+                                  rs.campos.reshape(3).float(), tail, bg, pad]).reshape(1, DM4D_VIEW_STRIDE)
+        return self._vp
+
+    @staticmethod
+    def _ident(*ts):
+        return tuple((weakref.ref(t), t._version) for t in ts)
+
+    def _plan_hit(self, *ts) -> Optional[RasterState]:
+        if self._plan is None:
+            return None
+        state, ident = self._plan
+        if state.overflowed or any(r() is not t or v != t._version for (r, v), t in zip(ident, ts)):
+            return None
+        return state
 
     def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
         """Frustum test of the replaced module (``mark_visible`` -> in_frustum): view-space depth > 0.2 (SURVEY.md
@@ -338,10 +503,22 @@ class GaussianRasterizer(nn.Module):
             # tensor ops, then rasterized as precomputed colours.  Reached by the reference only in predict_step
             # (system/base.py:257, degree 0); autograd supplies the gradients incl. the view-direction term.
             colors_precomp = sh_to_rgb(shs, means3D, rs.campos, int(rs.sh_degree))
-        vp = make_view_params(rs.viewmatrix.reshape(1, 4, 4), rs.projmatrix.reshape(1, 4, 4),
-                              rs.campos.reshape(1, 3), rs.tanfovx, rs.tanfovy, rs.bg.reshape(1, -1)[:, :3],
-                              rs.scale_modifier)
+        vp = self._view_params()
         m2d = None if means2D is None else means2D.reshape(1, -1, 3)
-        color, radii, depth, alpha = rasterize_batch(means3D, opacities, scales, rotations, colors_precomp, vp,
-                                                     rs.image_height, rs.image_width, means2D=m2d)
+        H, W = int(rs.image_height), int(rs.image_width)
+        plan = self._plan_hit(means3D, scales, rotations, opacities)
+        st: list = []
+        if plan is not None:
+            color, radii, depth, alpha = rasterize_batch(means3D, opacities, scales, rotations, colors_precomp, vp, H, W,
+                                                         means2D=m2d, capacity=plan.capacity, state_out=st, plan=plan)
+        else:
+            key = (means3D.shape[-2], H, W, 3, means3D.device.index)
+            cap = CAPACITY_BOOK.capacity(key)
+            color, radii, depth, alpha = rasterize_batch(means3D, opacities, scales, rotations, colors_precomp, vp, H, W,
+                                                         means2D=m2d, capacity=cap, state_out=st)
+            if cap is None:
+                CAPACITY_BOOK.note_exact(key, st[0].capacity)
+            else:
+                CAPACITY_BOOK.track(key, st[0])
+            self._plan = (st[0], self._ident(means3D, scales, rotations, opacities))
         return color[0], radii[0], depth[0], alpha[0]

@@ -31,8 +31,15 @@ class _SkinFunction(torch.autograd.Function):
             raise _lib.Dm4dError("dreammesh4d_b200 skinning needs CUDA tensors (there is no CPU path)")
         if faces.dtype != torch.int32 or nbr_idx.dtype != torch.int32:
             raise TypeError("faces / nbr_idx must be int32 (convert once at setup)")
-        nt, ns, nr, no = _f32(node_trans), _f32(node_scale).reshape(*node_scale.shape[:2], 9), _f32(node_rot), \
-            _f32(node_opacity).reshape(node_opacity.shape[0], -1)
+        # the reference hands out scale=None for dqs without d_scale and opacity=None unless hybrid
+        # (dynamic_sugar.py:144-145,401-404); the C ABI takes NULL for the inputs a method does not read
+        if node_scale is None and method != "dqs":
+            raise ValueError(f"skinning_method={method!r} needs node_scale")
+        if node_opacity is None and method == "hybrid":
+            raise ValueError("skinning_method='hybrid' needs node_opacity")
+        nt, nr = _f32(node_trans), _f32(node_rot)
+        ns = None if node_scale is None else _f32(node_scale).reshape(*node_scale.shape[:2], 9)
+        no = None if node_opacity is None else _f32(node_opacity).reshape(node_opacity.shape[0], -1)
         T, M = nt.shape[0], nt.shape[1]
         V, F, K, g = rest_verts.shape[0], faces.shape[0], nbr_idx.shape[1], bary.shape[0]
         P = F * g
@@ -51,7 +58,8 @@ class _SkinFunction(torch.autograd.Function):
         check(l.dm4d_skin_forward(ctypes.byref(d), ptr(verts), ptr(vert_rot), ptr(means), ptr(rots), ptr(normals),
                                   torch.cuda.current_stream().cuda_stream), "dm4d_skin_forward")
         ctx.desc, ctx.keep = d, keep + [verts, vert_rot]
-        ctx.shapes = (node_trans.shape, node_rot.shape, node_scale.shape, node_opacity.shape)
+        ctx.shapes = (node_trans.shape, node_rot.shape, None if node_scale is None else node_scale.shape,
+                      None if node_opacity is None else node_opacity.shape)
         ctx.want_normals = want_normals
         if not want_normals:
             normals = torch.empty(0, **f32)
@@ -80,8 +88,8 @@ class _SkinFunction(torch.autograd.Function):
                                    ptr(dn_r), ptr(dn_s), ptr(dn_o), torch.cuda.current_stream().cuda_stream),
               "dm4d_skin_backward")
         sh = ctx.shapes
-        return (dn_t.reshape(sh[0]), dn_r.reshape(sh[1]), dn_s.reshape(sh[2]), dn_o.reshape(sh[3]),
-                None, None, None, None, None, None, None, None)
+        return (dn_t.reshape(sh[0]), dn_r.reshape(sh[1]), None if sh[2] is None else dn_s.reshape(sh[2]),
+                None if sh[3] is None else dn_o.reshape(sh[3]), None, None, None, None, None, None, None, None)
 
 
 def skin_gaussians(node_trans, node_rot, node_scale, node_opacity, rest_verts, faces, nbr_idx, nbr_w, bary, rest_quat,

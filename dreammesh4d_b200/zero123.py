@@ -460,6 +460,28 @@ class Zero123Model(nn.Module):
         return self.model.diffusion_model(xc, t, cc)
 
 
+def build_random(cfg: Zero123Config = Zero123Config(), device="cuda", dtype: torch.dtype = torch.float16,
+                 seed: int = 0) -> Zero123Model:
+    """Random-weight model at the configured shapes, materialised directly on ``device`` in ``dtype`` (no 3.4 GB fp32
+    host copy): matrices / filters ~ N(0, 1/fan_in), norm scales 1, biases 0 — activations stay O(1), so the fp16
+    step does the arithmetic of the real model on finite numbers.  Offline stand-in for the Zero123 checkpoint
+    (``load_state_dict`` of the real one works on the same object, strict=True per prefix)."""
+    with torch.device("meta"):
+        m = Zero123Model(cfg)
+    m = m.to_empty(device=device).to(dtype)
+    g = torch.Generator(device=device).manual_seed(seed)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if p.dim() > 1:
+                p.normal_(0.0, 1.0 / math.sqrt(p[0].numel()), generator=g)
+            elif name.endswith("weight"):
+                p.fill_(1.0)
+            else:
+                p.zero_()
+            p.requires_grad_(False)
+    return m.eval()
+
+
 def unet_flops(cfg: UNetConfig, n: int, h: int, w: int, ctx_len: int = 1) -> float:
     """Multiply-add FLOPs (2 per MAC) of one UNet evaluation as EXECUTED here (single-token cross-attention shortcut
     included) on a batch of ``n`` latents of ``h x w``.  Walks the same block plan as the constructor."""

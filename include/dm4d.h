@@ -115,6 +115,22 @@ int dm4d_raster_render(const dm4d_raster_desc* d, float* out_color, float* out_d
 int dm4d_raster_forward(const dm4d_raster_desc* d, float* out_color, float* out_depth, float* out_alpha,
                         int32_t* radii, void* stream);
 
+/* Second pass over an already planned batch with OTHER per-Gaussian features (the reference's renderer calls the
+ * rasterizer twice per view with identical means / scales / rotations / opacities — RGB, then normals as colours,
+ * diff_sugar_rasterizer_temporal.py:169-178,202-211): re-uses projection, binning and the depth sort of `planned`
+ * (a desc on which dm4d_raster_forward ran), re-binds `d->colors` (/colors2) onto the sorted instance stream and
+ * composites.  `d` must equal `planned` in sizes, channels, bin_capacity and share its `geom` workspace; `d->bin`
+ * and `d->img` are its OWN workspaces (same sizes), so both passes keep what their backward needs.
+ * dm4d_raster_backward(d, ...) then works as after dm4d_raster_forward. */
+int dm4d_raster_render_features(const dm4d_raster_desc* planned, const dm4d_raster_desc* d, float* out_color,
+                                float* out_depth, float* out_alpha, void* stream);
+
+/* Status header: the first 16 bytes of the `bin` workspace are
+ *     struct { uint64_t num_rendered; uint32_t overflow; uint32_t pad; }
+ * written by the plan phase on the device.  A caller that must not synchronise (CUDA-graph replay, a training loop)
+ * reads or accumulates the flag with its own device-side ops and polls it every N steps; dm4d_raster_status is the
+ * synchronous convenience form.  When `overflow` is 1 the render and backward kernels treat every tile as empty
+ * (background images, zero gradients) — the caller must re-run with a larger capacity. */
 /* Synchronises `stream` and reports the instance count and overflow flag of the last plan. */
 int dm4d_raster_status(const dm4d_raster_desc* d, int64_t* num_rendered_host, int32_t* overflow_host,
                        void* stream);

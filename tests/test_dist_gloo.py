@@ -120,7 +120,7 @@ def _make_net():
     return net
 
 
-def _worker_step(rank, world, port, ret):
+def _worker_step(rank, world, port, ret, exchange):
     """DynamicStageStep with a process group: every rank steps on ITS batch; the parameters end up identical on all
     ranks and equal to a single-process step over the union of the batches (the reference's DDP semantics)."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -131,12 +131,17 @@ def _worker_step(rank, world, port, ret):
     loss_fn = lambda out, b: out["x"]
     # single-process reference over the union (no process group yet)
     net_ref = _make_net()
-    DynamicStageStep(_StubGeometry(net_ref, xyz), _StubRenderer(), torch.optim.SGD(net_ref.parameters(), lr=0.1), loss_fn)(batches, 0)
+    ref_step = DynamicStageStep(_StubGeometry(net_ref, xyz), _StubRenderer(), torch.optim.SGD(net_ref.parameters(), lr=0.1), loss_fn)
+    ref_step(batches, 0)
+    ref_step(batches, 1)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         net = _make_net()
-        step = DynamicStageStep(_StubGeometry(net, xyz), _StubRenderer(), torch.optim.SGD(net.parameters(), lr=0.1), loss_fn)
+        step = DynamicStageStep(_StubGeometry(net, xyz), _StubRenderer(), torch.optim.SGD(net.parameters(), lr=0.1), loss_fn,
+                                exchange=exchange)
+        assert (step.bucket is not None) == (exchange == "dense")
         step([batches[rank]], 0)
+        step([batches[rank]], 1)          # second step: the flat bucket is re-zeroed, not re-accumulated
         moved = sum(float((p - q).abs().max()) > 0 for p, q in zip(net.parameters(), _make_net().parameters()))
         same = all(torch.allclose(p, q, rtol=1e-5, atol=1e-7) for p, q in zip(net.parameters(), net_ref.parameters()))
         ret[rank] = bool(same and moved >= 8)
@@ -145,9 +150,10 @@ def _worker_step(rank, world, port, ret):
 
 
 @pytest.mark.timeout(180)
-def test_dynamic_stage_step_world2_gloo_equals_single_process_union():
+@pytest.mark.parametrize("exchange", ["dense", "node_gather"])
+def test_dynamic_stage_step_world2_gloo_equals_single_process_union(exchange):
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 33500 + (os.getpid() % 2000)
-    mp.spawn(_worker_step, args=(2, port, ret), nprocs=2, join=True)
+    port = 33500 + (os.getpid() % 2000) + (7 if exchange == "dense" else 0)
+    mp.spawn(_worker_step, args=(2, port, ret, exchange), nprocs=2, join=True)
     assert ret[0] and ret[1]
