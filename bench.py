@@ -39,7 +39,7 @@ import torch
 
 WORKLOAD = "C3: 100k-face sphere, 300k surface-bound Gaussians, 8 views x 8 timestamps per rank, 512x512, 1 pass (3ch) fwd+bwd"
 METRIC = "rasterize fwd+bwd Gaussians/s @512x512, 8 views/GPU"
-N_FACES, G_PER_FACE, H, W, VIEWS = 100_000, 3, 512, 512, 8
+N_FACES, G_PER_FACE, H, W, VIEWS = 100_000, 3, 512, 512, int(os.environ.get("DM4D_VIEWS", "8"))   # DM4D_VIEWS: tuning only
 M_NODES, K_NBR = 1000, 4
 
 
@@ -824,10 +824,22 @@ def run_ours(args):
         }
     if out is not None:
         print(json.dumps(out), flush=True)
-    if dist is not None:
-        torch.cuda.synchronize()
-        dist.destroy_process_group()
+    finish(dist)
     return None
+
+
+def finish(dist):
+    """End of a (possibly multi-rank) run.  With NCCL collectives captured in live CUDA graphs,
+    ``destroy_process_group`` can block forever in communicator teardown (seen at N=2: ten minutes until the watchdog);
+    the result line is already on stdout, so synchronise, meet at a barrier and leave without the teardown."""
+    if dist is None:
+        return
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -844,8 +856,7 @@ def run_c2(args):
         print(json.dumps({"metric": "train-step ms (dynamic stage incl. Zero123 SDS)", "value": train["ms_median"], "unit": "ms",
                           "n_gpus": world, "higher_is_better": False, "dtype": "f32 (raster/skinning) + f16 (Zero123)", "data": "synthetic",
                           "config": {"workload": train["label"]}, "train_step": train, "sds": sds, "clocks": sampler.result()}), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    finish(dist)
 
 
 def run_c4(args):
@@ -1020,7 +1031,7 @@ def run_reference(args):
 def main():
     import faulthandler
     faulthandler.enable()
-    faulthandler.dump_traceback_later(int(os.environ.get("DM4D_BENCH_WATCHDOG_S", "600")), exit=True)   # never hang a GPU box
+    faulthandler.dump_traceback_later(int(os.environ.get("DM4D_BENCH_WATCHDOG_S", "420")), exit=True)   # never hang a GPU box
     args = parse()
     if args.impl == "reference":
         # torchrun exports OMP_NUM_THREADS=1 for N>1 launches: the CPU arm is meant to use every host core

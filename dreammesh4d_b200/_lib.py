@@ -87,6 +87,8 @@ SIGNATURES = {
     "dm4d_hexplane_forward": (ctypes.c_int, [POINTER(HexplaneDesc), c_void_p, c_void_p]),
     "dm4d_hexplane_backward": (ctypes.c_int, [POINTER(HexplaneDesc), c_void_p, POINTER(c_void_p), c_void_p]),
     "dm4d_graph_knn": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "dm4d_groupnorm_nhwc_forward": (ctypes.c_int, [c_void_p] * 4 + [c_int32] * 4 + [ctypes.c_float] + [c_int32] * 2 + [c_void_p] * 4),
+    "dm4d_groupnorm_nhwc_backward": (ctypes.c_int, [c_void_p] * 5 + [c_int32] * 4 + [ctypes.c_float] + [c_int32] * 2 + [c_void_p] * 4),
     "dm4d_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "dm4d_profile_collect": (ctypes.c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
     "dm4d_kernel_name": (c_char_p, [ctypes.c_int]),
@@ -94,7 +96,7 @@ SIGNATURES = {
     "dm4d_version": (ctypes.c_int, []),
 }
 
-K_COUNT = 19
+K_COUNT = 21
 
 _lib = None
 

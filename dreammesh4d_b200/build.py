@@ -29,6 +29,7 @@ UNITS = {
     "postops.cu": [],
     "hexplane.cu": [],
     "graph.cu": [],
+    "nhwc_norm.cu": [],
     "capi.cu": [],
 }
 

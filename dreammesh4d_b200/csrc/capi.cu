@@ -204,7 +204,7 @@ const char* const kNames[DM4D_K_COUNT] = {
     "skin_gaussian_forward_kernel", "skin_gaussian_backward_kernel", "skin_vertex_backward_kernel",
     "sugar_rest_frames_kernel", "arap_energy_kernel", "normal_consistency_kernel", "postops_forward_kernel",
     "postops_backward_kernels", "hexplane_forward_kernel", "hexplane_backward_kernel",
-    "knn_kernel"};
+    "knn_kernel", "groupnorm_nhwc_forward_kernels", "groupnorm_nhwc_backward_kernels"};
 }  // namespace
 
 KernelTimer::KernelTimer(int id_, cudaStream_t s_) : id(id_), s(s_), on(g_prof_on), e0(nullptr) {

@@ -1,0 +1,88 @@
+"""Channels-last GroupNorm (+ channel bias, + SiLU) — autograd binding over dm4d_groupnorm_nhwc_forward / _backward.
+
+The glue between the tensor-core convolutions of the Zero123 networks in the SDS step: one fused
+pass replaces torch's NCHW-only GroupNorm, the separate SiLU, the time-embedding broadcast add and the NHWC<->NCHW
+transposes cuDNN otherwise inserts around every convolution (ResBlock, openaimodel.py:269-289; ResnetBlock,
+model.py:118-138 of the reference).  CUDA only; on other devices ``GroupNormAct`` evaluates the same formula with torch
+ops (the CPU parity tests of ``zero123.py`` run that way).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import check, ptr
+
+_DTYPES = {torch.float32: 0, torch.float16: 1}
+
+
+class _GroupNormNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, chan_bias, gamma, beta, groups, eps, silu):
+        N, C, H, W = x.shape
+        if x.dtype not in _DTYPES:
+            raise TypeError(f"groupnorm_nhwc: fp16 or fp32 activations, got {x.dtype}")
+        x = x.contiguous(memory_format=torch.channels_last)
+        cb = None if chan_bias is None else chan_bias.detach().float().contiguous()
+        f32 = dict(dtype=torch.float32, device=x.device)
+        stats = torch.empty(N, groups, 2, **f32)
+        scratch = torch.empty(N, groups, 2, **f32)
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        check(_lib.lib().dm4d_groupnorm_nhwc_forward(ptr(x), ptr(cb), ptr(gamma), ptr(beta), N, H * W, C, groups, float(eps),
+                                                     int(silu), _DTYPES[x.dtype], ptr(stats), ptr(scratch), ptr(y),
+                                                     torch.cuda.current_stream().cuda_stream), "dm4d_groupnorm_nhwc_forward")
+        ctx.save_for_backward(x, cb, gamma, beta, stats)
+        ctx.cfg = (groups, float(eps), int(silu))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, cb, gamma, beta, stats = ctx.saved_tensors
+        groups, eps, silu = ctx.cfg
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("groupnorm_nhwc: no gradient for the channel bias (frozen in the SDS step)")
+        N, C, H, W = x.shape
+        dy = dy.to(x.dtype).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        scratch = torch.empty(N, groups, 2, dtype=torch.float32, device=x.device)
+        check(_lib.lib().dm4d_groupnorm_nhwc_backward(ptr(x), ptr(cb), ptr(dy), ptr(gamma), ptr(beta), N, H * W, C, groups, eps, silu,
+                                                      _DTYPES[x.dtype], ptr(stats), ptr(scratch), ptr(dx),
+                                                      torch.cuda.current_stream().cuda_stream), "dm4d_groupnorm_nhwc_backward")
+        return dx, None, None, None, None, None, None
+
+
+def groupnorm_nhwc(x: torch.Tensor, gamma32: torch.Tensor, beta32: torch.Tensor, groups: int, eps: float, silu: bool,
+                   chan_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``act(GroupNorm(x + chan_bias[:, :, None, None]))`` on a channels-last [N,C,H,W] CUDA tensor (fp16 / fp32);
+    ``gamma32`` / ``beta32`` are fp32 [C].  Differentiable w.r.t. ``x`` only."""
+    return _GroupNormNHWC.apply(x, chan_bias, gamma32, beta32, groups, eps, silu)
+
+
+class GroupNormAct(nn.GroupNorm):
+    """``nn.GroupNorm`` (same parameters / state_dict keys) followed by an optional SiLU, with an optional per-sample
+    channel bias added in front; fused channels-last kernel on CUDA, torch ops elsewhere."""
+
+    def __init__(self, num_groups: int, num_channels: int, eps: float = 1e-5, silu: bool = False):
+        super().__init__(num_groups, num_channels, eps=eps, affine=True)
+        self.silu = silu
+        self._p32 = None
+
+    def _params32(self):
+        key = (self.weight._version, self.bias._version, self.weight.data_ptr(), self.weight.device)
+        if self._p32 is None or self._p32[0] != key:
+            self._p32 = (key, self.weight.detach().float().contiguous(), self.bias.detach().float().contiguous())
+        return self._p32[1], self._p32[2]
+
+    def forward(self, x: torch.Tensor, chan_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if x.is_cuda and x.dtype in _DTYPES and not (self.weight.requires_grad or self.bias.requires_grad) and \
+                self.num_channels % 4 == 0 and self.num_groups <= 64:
+            g32, b32 = self._params32()
+            return groupnorm_nhwc(x, g32, b32, self.num_groups, self.eps, self.silu, chan_bias)
+        if chan_bias is not None:
+            x = x + chan_bias.to(x.dtype)[:, :, None, None]
+        y = F.group_norm(x, self.num_groups, self.weight, self.bias, self.eps)
+        return F.silu(y) if self.silu else y

@@ -220,7 +220,9 @@ class _RasterizeBatch(torch.autograd.Function):
             check(l.dm4d_raster_forward(ctypes.byref(d), ptr(color), ptr(depth), ptr(alpha), ptr(radii), stream),
                   "dm4d_raster_forward")
 
-        state = RasterState(d, [m, sc, ro, op, co, c2, vp, geom, bin_, img, alpha], capacity)
+        # alpha.detach(): same storage and version counter, but no reference back to this node (no ctx <-> output cycle,
+        # so the workspaces are released by reference counting, not by the cyclic GC)
+        state = RasterState(d, [m, sc, ro, op, co, c2, vp, geom, bin_, img, alpha.detach()], capacity)
         state.radii = radii
         state.alpha_version = alpha._version      # the backward reads T_final = 1 - alpha from this very tensor
         ctx.state = state

@@ -76,6 +76,9 @@ class TemporalStableZero123SDS:
                  weights_dtype: torch.dtype = torch.float16, num_train_timesteps: int = 1000,
                  linear_start: float = 0.00085, linear_end: float = 0.0120):
         self.model = model
+        if isinstance(model, torch.nn.Module):
+            for p in model.parameters():            # guidance :124-125 — the diffusion prior is frozen
+                p.requires_grad_(False)
         self.weights_dtype = weights_dtype
         self.device = c_crossattn.device
         self.c_crossattn = c_crossattn.to(weights_dtype)

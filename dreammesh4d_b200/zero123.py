@@ -32,6 +32,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .nhwc import GroupNormAct
+
 
 # --------------------------------------------------------------------------------------------------------------------
 # configuration (load/zero123/sd-objaverse-finetune-c_concat-256.yaml:28-60)
@@ -108,16 +110,16 @@ class TimeResBlock(nn.Module):
 
     def __init__(self, cin: int, cout: int, emb: int, groups: int):
         super().__init__()
-        self.in_layers = Slots({0: nn.GroupNorm(groups, cin), 2: nn.Conv2d(cin, cout, 3, padding=1)})
+        self.in_layers = Slots({0: GroupNormAct(groups, cin, silu=True), 2: nn.Conv2d(cin, cout, 3, padding=1)})
         self.emb_layers = Slots({1: nn.Linear(emb, cout)})
-        self.out_layers = Slots({0: nn.GroupNorm(groups, cout), 3: nn.Conv2d(cout, cout, 3, padding=1)})
+        self.out_layers = Slots({0: GroupNormAct(groups, cout, silu=True), 3: nn.Conv2d(cout, cout, 3, padding=1)})
         self.skip_connection = nn.Identity() if cin == cout else nn.Conv2d(cin, cout, 1)
 
     def forward(self, x: torch.Tensor, act_emb: torch.Tensor) -> torch.Tensor:
-        """``act_emb`` = SiLU(time embedding), computed once per network evaluation by the caller."""
-        h = self.in_layers[2](F.silu(self.in_layers[0](x)))
-        h = h + self.emb_layers[1](act_emb)[:, :, None, None]
-        h = self.out_layers[3](F.silu(self.out_layers[0](h)))
+        """``act_emb`` = SiLU(time embedding), computed once per network evaluation by the caller.  Norm + SiLU (and the
+        time-embedding add in front of the second norm) are one fused channels-last pass each (nhwc.py)."""
+        h = self.in_layers[2](self.in_layers[0](x))
+        h = self.out_layers[3](self.out_layers[0](h, chan_bias=self.emb_layers[1](act_emb)))
         return self.skip_connection(x) + h
 
 
@@ -182,14 +184,14 @@ class SpatialTransformer(nn.Module):
 
     def __init__(self, ch: int, heads: int, ctx_dim: int, groups: int):
         super().__init__()
-        self.norm = nn.GroupNorm(groups, ch, eps=1e-6)
+        self.norm = GroupNormAct(groups, ch, eps=1e-6)
         self.proj_in = nn.Conv2d(ch, ch, 1)
         self.transformer_blocks = nn.ModuleList([TransformerBlock(ch, heads, ctx_dim)])
         self.proj_out = nn.Conv2d(ch, ch, 1)
 
     def forward(self, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
         B, C, H, W = x.shape
-        h = _nhwc(self.norm(x).contiguous(memory_format=torch.channels_last))       # [B,H,W,C] view, no copy
+        h = _nhwc(self.norm(x).contiguous(memory_format=torch.channels_last))       # [B,H,W,C] view (no copy on CUDA)
         t = _pointwise(self.proj_in, h).reshape(B, H * W, C)
         for blk in self.transformer_blocks:
             t = blk(t, context)
@@ -287,7 +289,7 @@ class Zero123UNet(nn.Module):
                     ds //= 2
                 ups.append(Stage(layers))
         self.output_blocks = nn.ModuleList(ups)
-        self.out = Slots({0: nn.GroupNorm(g, ch), 2: nn.Conv2d(mc, cfg.out_channels, 3, padding=1)})
+        self.out = Slots({0: GroupNormAct(g, ch, silu=True), 2: nn.Conv2d(mc, cfg.out_channels, 3, padding=1)})
 
     def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
         """x [N,in_channels,h,w], timesteps [N], context [N,L,context_dim] -> [N,out_channels,h,w] (openaimodel.py:810-842)."""
@@ -303,8 +305,7 @@ class Zero123UNet(nn.Module):
         h = self.middle_block(h, act_emb, context)
         for st in self.output_blocks:
             h = st(torch.cat([h, hs.pop()], dim=1), act_emb, context)
-        h = h.to(x.dtype)
-        return self.out[2](F.silu(self.out[0](h)))
+        return self.out[2](self.out[0](h)).to(x.dtype)
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -315,16 +316,16 @@ class VAEResBlock(nn.Module):
 
     def __init__(self, cin: int, cout: int, groups: int):
         super().__init__()
-        self.norm1 = nn.GroupNorm(groups, cin, eps=1e-6)
+        self.norm1 = GroupNormAct(groups, cin, eps=1e-6, silu=True)
         self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
-        self.norm2 = nn.GroupNorm(groups, cout, eps=1e-6)
+        self.norm2 = GroupNormAct(groups, cout, eps=1e-6, silu=True)
         self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
         if cin != cout:
             self.nin_shortcut = nn.Conv2d(cin, cout, 1)
 
     def forward(self, x):
-        h = self.conv1(F.silu(self.norm1(x)))
-        h = self.conv2(F.silu(self.norm2(h)))
+        h = self.conv1(self.norm1(x))
+        h = self.conv2(self.norm2(h))
         return (self.nin_shortcut(x) if hasattr(self, "nin_shortcut") else x) + h
 
 
@@ -333,7 +334,7 @@ class VAEAttention(nn.Module):
 
     def __init__(self, ch: int, groups: int):
         super().__init__()
-        self.norm = nn.GroupNorm(groups, ch, eps=1e-6)
+        self.norm = GroupNormAct(groups, ch, eps=1e-6)
         self.q, self.k, self.v, self.proj_out = (nn.Conv2d(ch, ch, 1) for _ in range(4))
 
     def forward(self, x):
@@ -377,7 +378,7 @@ class Zero123Encoder(nn.Module):
         self.mid.block_1 = VAEResBlock(cin, cin, g)
         self.mid.attn_1 = VAEAttention(cin, g)
         self.mid.block_2 = VAEResBlock(cin, cin, g)
-        self.norm_out = nn.GroupNorm(g, cin, eps=1e-6)
+        self.norm_out = GroupNormAct(g, cin, eps=1e-6, silu=True)
         self.conv_out = nn.Conv2d(cin, 2 * cfg.z_channels, 3, padding=1)
 
     def forward(self, x):
@@ -388,7 +389,7 @@ class Zero123Encoder(nn.Module):
             if hasattr(level, "downsample"):
                 h = level.downsample(h)
         h = self.mid.block_2(self.mid.attn_1(self.mid.block_1(h)))
-        return self.conv_out(F.silu(self.norm_out(h)))
+        return self.conv_out(self.norm_out(h))
 
 
 class DiagonalGaussian:
@@ -468,7 +469,7 @@ def build_random(cfg: Zero123Config = Zero123Config(), device="cuda", dtype: tor
     (``load_state_dict`` of the real one works on the same object, strict=True per prefix)."""
     with torch.device("meta"):
         m = Zero123Model(cfg)
-    m = m.to_empty(device=device).to(dtype)
+    m = m.to_empty(device=device).to(dtype).to(memory_format=torch.channels_last)    # NHWC filters: no cuDNN transposes
     g = torch.Generator(device=device).manual_seed(seed)
     with torch.no_grad():
         for name, p in m.named_parameters():

@@ -283,6 +283,26 @@ int dm4d_hexplane_backward(const dm4d_hexplane_desc* d, const float* dL_dfeature
 int dm4d_graph_knn(const float* queries, int32_t n_queries, const float* nodes, int32_t n_nodes, int32_t k,
                    int32_t* idx, float* sqdist, void* stream);
 
+/* ---- channels-last GroupNorm (+ channel bias in front, + SiLU behind) for the Zero123 networks of the SDS step --------
+ * (SURVEY.md §8 row A9).  Replaces, between the tensor-core convolutions that stay library calls, the
+ * ``normalization(ch) -> SiLU`` pairs of ResBlock (extern/ldm_zero123/modules/diffusionmodules/openaimodel.py:210-214,
+ * 243-250,269-289; the time-embedding add ``h + emb_out`` :286 is the channel bias) and of ResnetBlock / Encoder
+ * (.../diffusionmodules/model.py:118-138,489-492), and the plain GroupNorm of SpatialTransformer / AttnBlock
+ * (modules/attention.py:275, model.py:169):
+ *     y[n,p,c] = act(((x[n,p,c] + chan_bias[n,c]) - mean[n,g]) * rstd[n,g] * gamma[c] + beta[c]),  g = c / (C/G)
+ * x, y: [N, HW, C] = the memory of a torch channels_last [N,C,H,W] tensor, `dtype` DM4D_F16 or DM4D_F32.
+ * chan_bias [N,C] fp32 or NULL; gamma, beta [C] fp32; stats [N,G,2] fp32 (mean, rstd; output of the forward, input of
+ * the backward); scratch [N,G,2] fp32.  C % G == 0, C % 4 == 0, C <= 4096, G <= 64. */
+#define DM4D_F32 0
+#define DM4D_F16 1
+int dm4d_groupnorm_nhwc_forward(const void* x, const float* chan_bias, const float* gamma, const float* beta,
+                                int32_t N, int32_t HW, int32_t C, int32_t G, float eps, int32_t silu, int32_t dtype,
+                                float* stats, float* scratch, void* y, void* stream);
+/* dx (same layout / dtype as x) from dy; gamma / beta / chan_bias receive no gradient (frozen in the SDS step). */
+int dm4d_groupnorm_nhwc_backward(const void* x, const float* chan_bias, const void* dy, const float* gamma,
+                                 const float* beta, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, int32_t silu,
+                                 int32_t dtype, const float* stats, float* scratch, void* dx, void* stream);
+
 /* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel launch).
  * Kernel ids: see DM4D_K_* below.  dm4d_profile_collect synchronises the recorded events, ADDS the
  * elapsed milliseconds / launch counts since the last collect into ms[DM4D_K_COUNT] /
@@ -292,7 +312,7 @@ enum {
     DM4D_K_RENDER_BWD, DM4D_K_PREPROCESS_BWD, DM4D_K_SKIN_VERT_FWD, DM4D_K_SKIN_GAUSS_FWD,
     DM4D_K_SKIN_GAUSS_BWD, DM4D_K_SKIN_VERT_BWD, DM4D_K_REST_FRAMES, DM4D_K_ARAP, DM4D_K_NORMAL_CONS,
     DM4D_K_POSTOPS_FWD, DM4D_K_POSTOPS_BWD, DM4D_K_HEXPLANE_FWD, DM4D_K_HEXPLANE_BWD,
-    DM4D_K_GRAPH_KNN, DM4D_K_COUNT
+    DM4D_K_GRAPH_KNN, DM4D_K_GROUPNORM_FWD, DM4D_K_GROUPNORM_BWD, DM4D_K_COUNT
 };
 int dm4d_profile_enable(int on);
 int dm4d_profile_collect(double* ms_host, int64_t* launches_host);
