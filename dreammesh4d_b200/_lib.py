@@ -74,7 +74,7 @@ SIGNATURES = {
     "dm4d_raster_forward": (ctypes.c_int, [POINTER(RasterDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dm4d_raster_render_features": (ctypes.c_int, [POINTER(RasterDesc), POINTER(RasterDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
     "dm4d_raster_status": (ctypes.c_int, [POINTER(RasterDesc), POINTER(c_int64), POINTER(c_int32), c_void_p]),
-    "dm4d_raster_backward": (ctypes.c_int, [POINTER(RasterDesc)] + [c_void_p] * 12),
+    "dm4d_raster_backward": (ctypes.c_int, [POINTER(RasterDesc)] + [c_void_p] * 14),
     "dm4d_raster_export_state": (ctypes.c_int, [POINTER(RasterDesc), c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "dm4d_skin_forward": (ctypes.c_int, [POINTER(SkinDesc)] + [c_void_p] * 6),
     "dm4d_skin_backward": (ctypes.c_int, [POINTER(SkinDesc)] + [c_void_p] * 14),

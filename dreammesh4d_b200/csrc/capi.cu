@@ -16,7 +16,7 @@ void dm4d_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* dm4d_last_error(void) { return g_err; }
-extern "C" int dm4d_version(void) { return 120; }   // 1.2: + raster_render_features (plan reuse), status header
+extern "C" int dm4d_version(void) { return 130; }   // 1.3: segmented front-to-back backward (takes the forward's colour / depth images), groupnorm_nhwc
 
 void raster_sizes(int P, int H, int W, int n_views, int channels, long long capacity, uint64_t* geom, uint64_t* bin,
                   uint64_t* img, uint64_t* bwd) {
@@ -24,9 +24,12 @@ void raster_sizes(int P, int H, int W, int n_views, int channels, long long capa
     const uint64_t nt = (uint64_t)n_views * gx * gy, np = (uint64_t)n_views * P;
     const int rec = rec_floats(channels), acc = acc_floats(channels);
     if (geom) *geom = 256 + align_up(np * rec * 4, 256) + align_up(np * 4, 256);   // never zero-sized
+    const uint64_t segs = (uint64_t)seg_capacity(capacity, (long long)nt);
     if (bin)
         *bin = 256 + align_up(nt * 4, 256) + align_up((nt + 1) * 4, 256) + align_up(nt * 4, 256) + align_up(nt * 4, 256) +
-               align_up((uint64_t)capacity * 8, 256) + align_up((uint64_t)capacity * rec * 4, 256);
+               align_up((nt + 1) * 4, 256) + align_up(segs * 4, 256) +
+               align_up((uint64_t)capacity * 8, 256) + align_up((uint64_t)capacity * rec * 4, 256) +
+               align_up(segs * 256 * ckpt_floats(channels) * 4, 256);
     if (img) *img = align_up((uint64_t)n_views * H * W * 4, 256);
     if (bwd) *bwd = 256 + align_up(np * acc * 4, 256);
 }
@@ -73,8 +76,12 @@ int raster_make_layout(const dm4d_raster_desc* d, RasterLayout* L) {
     L->tile_offset = (unsigned int*)p; p += align_up((nt + 1) * 4, 256);
     L->tile_cursor = (unsigned int*)p; p += align_up(nt * 4, 256);
     L->tile_order = (unsigned int*)p; p += align_up(nt * 4, 256);
+    L->seg_cap = seg_capacity(L->capacity, (long long)nt);
+    L->seg_offset = (unsigned int*)p; p += align_up((nt + 1) * 4, 256);
+    L->seg_tile = (unsigned int*)p; p += align_up((uint64_t)L->seg_cap * 4, 256);
     L->keys = (unsigned long long*)p; p += align_up((uint64_t)L->capacity * 8, 256);
-    L->stream = (float*)p;
+    L->stream = (float*)p; p += align_up((uint64_t)L->capacity * L->rec * 4, 256);
+    L->ckpt = (float*)p;
     L->n_contrib = (unsigned int*)d->img;
     L->accum = (float*)d->bwd;
     return DM4D_OK;
@@ -159,7 +166,8 @@ extern "C" int dm4d_raster_status(const dm4d_raster_desc* d, int64_t* num_render
     return DM4D_OK;
 }
 
-extern "C" int dm4d_raster_backward(const dm4d_raster_desc* d, const float* out_alpha, const float* dL_dcolor,
+extern "C" int dm4d_raster_backward(const dm4d_raster_desc* d, const float* out_color, const float* out_depth,
+                                    const float* out_alpha, const float* dL_dcolor,
                                     const float* dL_ddepth, const float* dL_dalpha, float* dL_dmeans3D,
                                     float* dL_dmeans2D, float* dL_dcolors, float* dL_dcolors2, float* dL_dopacities,
                                     float* dL_dscales, float* dL_drotations, void* stream) {
@@ -169,10 +177,10 @@ extern "C" int dm4d_raster_backward(const dm4d_raster_desc* d, const float* out_
     uint64_t bwd;
     raster_sizes(d->P, d->H, d->W, d->n_views, d->channels, d->bin_capacity, nullptr, nullptr, nullptr, &bwd);
     if (!d->bwd || d->bwd_bytes < bwd) { dm4d_set_error("bwd workspace too small: need %llu", (unsigned long long)bwd); return DM4D_ENOSPC; }
-    if (!out_alpha || !dL_dcolor) { dm4d_set_error("out_alpha / dL_dcolor is NULL"); return DM4D_EINVAL; }
+    if (!out_color || !out_depth || !out_alpha || !dL_dcolor) { dm4d_set_error("out_color / out_depth / out_alpha / dL_dcolor is NULL"); return DM4D_EINVAL; }
     if (d->P == 0) return DM4D_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    if ((rc = launch_render_backward(d, L, out_alpha, dL_dcolor, dL_ddepth, dL_dalpha, s))) return rc;
+    if ((rc = launch_render_backward(d, L, out_color, out_depth, out_alpha, dL_dcolor, dL_ddepth, dL_dalpha, s))) return rc;
     return launch_preprocess_backward(d, L, dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dcolors2, dL_dopacities,
                                       dL_dscales, dL_drotations, s);
 }

@@ -62,6 +62,46 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(RasterLayout L
         L.hdr->total = total;
         L.hdr->overflow = ((long long)total > L.capacity) ? 1u : 0u;
     }
+    // Segment tables of the backward: exclusive scan of ceil(count / DM4D_SEG) and the segment -> tile map.
+    __syncthreads();
+    {
+        unsigned int lseg = 0;
+        for (int i = beg; i < end; ++i) lseg += (L.tile_count[i] + DM4D_SEG - 1) / DM4D_SEG;
+        unsigned int sincl = lseg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int t = __shfl_up_sync(0xffffffffu, sincl, o);
+            if (lane >= o) sincl += t;
+        }
+        if (lane == 31) warp_sums[wid] = sincl;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned int w = warp_sums[lane];
+            unsigned int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_sums[lane] = wi - w;
+            if (lane == 31) carry_s = wi;
+        }
+        __syncthreads();
+        unsigned int srun = warp_sums[wid] + (sincl - lseg);
+        const bool fits = (long long)carry_s <= L.seg_cap && !((long long)L.tile_offset[n] > L.capacity);
+        for (int i = beg; i < end; ++i) {
+            L.seg_offset[i] = srun;
+            const unsigned int ns = (L.tile_count[i] + DM4D_SEG - 1) / DM4D_SEG;
+            if (fits)
+                for (unsigned int k = 0; k < ns; ++k) L.seg_tile[srun + k] = (unsigned int)i;
+            srun += ns;
+        }
+        if (tid == 0) {
+            L.seg_offset[n] = carry_s;
+            L.hdr->total_segs = fits ? carry_s : 0u;
+        }
+        __syncthreads();
+    }
     // Launch order of the per-tile CTAs: heaviest tiles first (counting sort on floor(log2(count))), so the
     // long limb/centre tiles do not form the tail of the render kernels.
     if (tid < 33) bucket_cnt[tid] = 0u;

@@ -6,10 +6,10 @@
 
 #define DM4D_BLOCK 256
 
-// Height of a culling cell (cells are 4 pixels wide).  4 (default, validated): 4x4 cells, one instance queue per
-// HALF-warp, 16-bit masks.  2 (EXPERIMENTAL, prepared at the end of round 1 and not yet run on a GPU): 4x2 cells, one
-// queue per QUARTER-warp, 32-bit masks — 1.07 instead of 1.21 warp iterations per instance in the CPU simulation
-// (scripts/sim_cell_queues.py).  raster_binning.cu (mask) and raster_render.cu (queues, reductions) must agree.
+// Height of a culling cell (cells are 4 pixels wide): 4x4 cells, one instance queue per HALF-warp, 16-bit masks.
+// A 4x2 variant (quarter-warp queues, 32-bit masks) was built and measured in round 2: parity green, step time
+// 2.064 -> 2.006 ms (-3 %, profiles/r2a_tune_cells4x2_fastexp.txt) — not worth the second code path, whose render side
+// was removed; the mask generator in raster_binning.cu still takes the cell height as a parameter.
 #ifndef DM4D_CELL_ROWS
 #define DM4D_CELL_ROWS 4
 #endif
@@ -17,8 +17,18 @@
 struct BinHeader {
     unsigned long long total;   // R = number of (Gaussian, tile) instances over all views
     unsigned int overflow;      // 1 if R > capacity (nothing rendered)
-    unsigned int pad;
+    unsigned int total_segs;    // number of (tile, segment) work items of the backward (see DM4D_SEG)
 };
+
+// The backward splits every tile's depth-sorted instance list into SEGMENTS of DM4D_SEG instances that are processed
+// independently (front to back, starting from the compositing state the forward checkpointed at the segment's first
+// instance), so the serial chain of a heavy tile is bounded by one segment instead of the whole list.
+#ifndef DM4D_SEG
+#define DM4D_SEG 1024
+#endif
+__host__ __device__ inline long long seg_capacity(long long capacity, long long n_tiles) { return capacity / DM4D_SEG + n_tiles + 1; }
+// checkpoint of one (segment, pixel): C accumulated features, accumulated depth, transmittance
+__host__ __device__ inline int ckpt_floats(int channels) { return channels + 2; }
 
 // Projected per-(view, Gaussian) record; also the element of the sorted instance stream.
 //   f[0..3]  = x, y, conic.x, conic.y
@@ -46,6 +56,10 @@ struct RasterLayout {
     unsigned int* tile_offset;  // [n_views*tiles + 1]
     unsigned int* tile_cursor;  // [n_views*tiles]
     unsigned int* tile_order;   // [n_views*tiles] (view,tile) indices, heaviest tiles first (CTA launch order)
+    unsigned int* seg_offset;   // [n_views*tiles + 1] first segment index of each (view,tile): exclusive scan of ceil(count / DM4D_SEG)
+    unsigned int* seg_tile;     // [seg_cap] (view,tile) index of every segment
+    long long seg_cap;          // capacity / DM4D_SEG + n_views*tiles
+    float* ckpt;                // [seg_cap][channels+2][256] forward state at the first instance of every segment > 0 of its tile
     unsigned long long* keys;   // [capacity]  (depth bits << 32) | gaussian id
     float* stream;              // [capacity*rec] sorted instance records
     // img
@@ -80,8 +94,9 @@ int launch_scan(const RasterLayout& L, cudaStream_t s);
 int launch_scatter_sort_pack(const RasterLayout& L, cudaStream_t s);
 int launch_render_forward(const dm4d_raster_desc* d, const RasterLayout& L, float* out_color, float* out_depth,
                           float* out_alpha, cudaStream_t s);
-int launch_render_backward(const dm4d_raster_desc* d, const RasterLayout& L, const float* out_alpha,
-                           const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, cudaStream_t s);
+int launch_render_backward(const dm4d_raster_desc* d, const RasterLayout& L, const float* out_color, const float* out_depth,
+                           const float* out_alpha, const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                           cudaStream_t s);
 int launch_rebind_features(const dm4d_raster_desc* d, const RasterLayout& src, const RasterLayout& dst, cudaStream_t s);
 int launch_export_state(const RasterLayout& L, int view, unsigned int* ranges, unsigned int* point_list,
                         long long cap, unsigned int* n_contrib, cudaStream_t s);

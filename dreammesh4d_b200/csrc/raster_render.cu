@@ -14,12 +14,25 @@
 // (Gaussian, tile) instance at C3), so the unit of culling is the 4x4 cell: per chunk of 64 staged
 // instances the lanes ballot the instances' 16-bit cell masks and each half-warp walks its OWN queue of
 // instances that can reach its cell — the two halves run in lockstep on different instances, which cuts
-// the walked (warp, instance) iterations from 1.91 (16x2 strips) to about 1.2 per instance.  The
-// backward walks the same stream back to front, reduces the per-pixel partial gradients across the 16
-// lanes of the half-warp with a recursive-halving shuffle reduction (11 shuffles for the 10 sums of the
-// 3-channel pass, 15 for 6 channels; only when a lane contributes) and issues ONE coalesced global
-// reduction (RED.ADD.F32, one accumulator row) per (half-warp, instance) instead of upstream's ten
-// global atomics per (pixel, instance).
+// the walked (warp, instance) iterations from 1.91 (16x2 strips) to about 1.2 per instance.
+//
+// Backward.  Three ideas, each measured (profiles/):
+//  * SEGMENTS.  The forward checkpoints every pixel's compositing state (C, D, T) at each DM4D_SEG-th instance of its
+//    tile's list; the backward processes (tile, segment, 8x4 block) work items independently, so the serial chain of
+//    a heavy tile (6000 instances at C3: 0.4 ms for ONE warp = the whole duration of a single-view launch) is bounded
+//    by one segment.  A segment starts at its END with the state "behind" it: for pixels whose contributors stop
+//    inside the segment that is (T_final, background) exactly as in the replaced rasterizer; for the others it
+//    follows from the next segment's checkpoint and the forward's output images.
+//  * ONE SCALAR RECURRENCE.  With s_k = c_k . dL/dC + depth_k dL/dD + dL/dA the back-to-front recurrences of the
+//    replaced rasterizer (accum_rec[C], accum_d, accum_a, last_*) collapse into
+//    Q_{j-1} = alpha_j s_j + (1 - alpha_j) Q_j,   dL/dalpha_j = T_j (s_j - Q_j),   Q_end = bg . dL/dC.
+//  * NO CROSS-LANE REDUCTION.  ncu on the round-1 kernel: 175 warp instructions per (warp, instance) step, 40 % of
+//    them the shuffle / select / add tree that sums ten partial gradients over the 16 pixels of a cell, with a third
+//    of the lanes contributing.  Now the pixel-parallel sweep only evaluates alpha, advances (T, Q) and drops two
+//    numbers per pixel — h = G dL/dalpha and w = alpha T — into shared memory; after up to 16 steps the warp switches
+//    roles: every LANE takes one (cell, instance) pair and sums its 16 pixels in registers (all gradients of an
+//    instance are moments of h and w over the pixel offsets), then issues three 16-byte vector reductions
+//    (REDG.E.ADD.F32x4) on the instance's accumulator row.
 #include "raster_internal.cuh"
 
 namespace {
@@ -69,7 +82,6 @@ __device__ __forceinline__ float fast_rcp(float x) {
     return r;
 }
 
-#if DM4D_CELL_ROWS == 4
 // Pixel owned by a thread: warp w covers the 8x4 block (w & 1, w >> 1); its half-warp h covers the 4x4 cell
 // (cx, cy) = (2 (w & 1) + h, w >> 1), whose bit in an instance's cell mask is cy * 4 + cx = 2 w + h.
 struct PixelMap {
@@ -82,22 +94,6 @@ struct PixelMap {
         cell_bit = 2 * warp + half;
     }
 };
-#else
-// EXPERIMENTAL 4x2 cells: warp w covers the 8x4 block (w & 1, w >> 1); its quarter-warp g = lane / 8 covers the 4x2
-// cell (cx, cy8) = (2 (w & 1) + (g & 1), 2 (w >> 1) + (g >> 1)) of the tile's 4 x 8 cells; mask bit 4 cy8 + cx.
-// `half` holds the group index g, `li` the lane within the group (0..7).
-struct PixelMap {
-    int px, py, cell_bit, half, li;
-    __device__ __forceinline__ PixelMap(int tile_x, int tile_y, int warp, int lane) {
-        half = lane >> 3;
-        li = lane & 7;
-        const int cx = ((warp & 1) << 1) | (half & 1), cy8 = ((warp >> 1) << 1) | (half >> 1);
-        px = tile_x * DM4D_TILE + (cx << 2) + (li & 3);
-        py = tile_y * DM4D_TILE + (cy8 << 1) + (li >> 2);
-        cell_bit = 4 * cy8 + cx;
-    }
-};
-#endif
 
 // Candidate queue of this lane's half-warp for one staged chunk of 64 instances: bit j set <=> instance j of the chunk
 // can reach the half-warp's cell.  Four warp ballots (two cells x two 32-instance groups); uniform within a half-warp.
@@ -106,15 +102,6 @@ struct CellQueue {
     unsigned int lo, hi;
     __device__ __forceinline__ bool empty() const { return (lo | hi) == 0u; }
     __device__ __forceinline__ void clear() { lo = hi = 0u; }
-    // front to back (forward): lowest set bit, or -1
-    __device__ __forceinline__ int pop_front() {
-        const bool in_lo = lo != 0u;
-        unsigned int cur = in_lo ? lo : hi;
-        const int j = cur ? (__ffs((int)cur) - 1 + (in_lo ? 0 : 32)) : -1;
-        cur &= cur - 1u;
-        if (in_lo) lo = cur; else hi = cur;
-        return j;
-    }
     // back to front (backward): highest set bit; the queue must not be empty
     __device__ __forceinline__ int pop_back() {
         const bool in_hi = hi != 0u;
@@ -124,9 +111,17 @@ struct CellQueue {
         if (in_hi) hi = cur; else lo = cur;
         return b + (in_hi ? 32 : 0);
     }
+    // front to back: lowest set bit, or -1
+    __device__ __forceinline__ int pop_front() {
+        const bool in_lo = lo != 0u;
+        unsigned int cur = in_lo ? lo : hi;
+        const int j = cur ? (__ffs((int)cur) - 1 + (in_lo ? 0 : 32)) : -1;
+        cur &= cur - 1u;
+        if (in_lo) lo = cur; else hi = cur;
+        return j;
+    }
 };
 
-#if DM4D_CELL_ROWS == 4
 template <int R4>
 __device__ __forceinline__ CellQueue cell_queue(const float4* r, int cnt, int lane, int warp, int half) {
     const unsigned int m0 = lane < cnt ? __float_as_uint(r[lane * R4 + 1].z) : 0u;
@@ -139,23 +134,6 @@ __device__ __forceinline__ CellQueue cell_queue(const float4* r, int cnt, int la
     q.hi = half ? b1 : a1;
     return q;
 }
-#else
-// EXPERIMENTAL 4x2 cells: four queues per warp (one per quarter-warp), eight ballots per chunk.
-template <int R4>
-__device__ __forceinline__ CellQueue cell_queue(const float4* r, int cnt, int lane, int warp, int grp) {
-    const unsigned int m0 = lane < cnt ? __float_as_uint(r[lane * R4 + 1].z) : 0u;
-    const unsigned int m1 = lane + 32 < cnt ? __float_as_uint(r[(lane + 32) * R4 + 1].z) : 0u;
-    CellQueue q;
-    q.lo = q.hi = 0u;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const int bit = 4 * ((((warp >> 1) << 1) | (g >> 1))) + (((warp & 1) << 1) | (g & 1));
-        const unsigned int lo = __ballot_sync(0xffffffffu, (m0 >> bit) & 1u), hi = __ballot_sync(0xffffffffu, (m1 >> bit) & 1u);
-        if (g == grp) { q.lo = lo; q.hi = hi; }
-    }
-    return q;
-}
-#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -210,16 +188,16 @@ __device__ __forceinline__ void load_features(const float4* r, float (&f)[C], fl
 }
 
 // Per-warp streaming ring -------------------------------------------------------------------------
-template <int C>
+template <int C, int CHUNK = WCHUNK>
 struct WarpRing {
     using TR = RecTraits<C>;
-    float4* buf;        // [WSTAGES][WCHUNK * R4]
+    float4* buf;        // [WSTAGES][CHUNK * R4]
     uint64_t* full;     // [WSTAGES]
     const float* stream;
     int n;              // instances available in the tile
     __device__ __forceinline__ void init(unsigned char* smem_raw, int warp, int lane, const float* stream_, int n_) {
-        buf = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * WSTAGES * WCHUNK * TR::R4;
-        full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * WSTAGES * WCHUNK * TR::REC * sizeof(float)) + warp * WSTAGES;
+        buf = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * WSTAGES * CHUNK * TR::R4;
+        full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * WSTAGES * CHUNK * TR::REC * sizeof(float)) + warp * WSTAGES;
         stream = stream_;
         n = n_;
         if (lane == 0) {
@@ -228,19 +206,19 @@ struct WarpRing {
         }
         __syncwarp();
     }
-    // lane 0 only: stage chunk `c` (instances [c*WCHUNK, ...)) into slot `slot`
+    // lane 0 only: stage chunk `c` (instances [c*CHUNK, ...)) into slot `slot`
     __device__ __forceinline__ void issue(int c, int slot) {
-        const int cnt = min(WCHUNK, n - c * WCHUNK);
+        const int cnt = min(CHUNK, n - c * CHUNK);
         const uint32_t bytes = (uint32_t)cnt * TR::REC * sizeof(float);
         mbar_expect_tx(&full[slot], bytes);
-        bulk_g2s(buf + (size_t)slot * WCHUNK * TR::R4, stream + (size_t)c * WCHUNK * TR::REC, bytes, &full[slot]);
+        bulk_g2s(buf + (size_t)slot * CHUNK * TR::R4, stream + (size_t)c * CHUNK * TR::REC, bytes, &full[slot]);
     }
     __device__ __forceinline__ const float4* wait(int slot, int use) {
         mbar_wait(&full[slot], (uint32_t)use & 1u);
-        return buf + (size_t)slot * WCHUNK * TR::R4;
+        return buf + (size_t)slot * CHUNK * TR::R4;
     }
     static constexpr size_t smem_bytes() {
-        return (size_t)WARPS * WSTAGES * WCHUNK * TR::REC * sizeof(float) + (size_t)WARPS * WSTAGES * sizeof(uint64_t);
+        return (size_t)WARPS * WSTAGES * CHUNK * TR::REC * sizeof(float) + (size_t)WARPS * WSTAGES * sizeof(uint64_t);
     }
 };
 
@@ -285,6 +263,14 @@ __global__ void __launch_bounds__(THREADS) render_forward_kernel(RasterLayout L,
         int c = 0;
         for (; c < nchunks; ++c) {
             const int slot = c % WSTAGES;
+            if (c > 0 && (c * WCHUNK) % DM4D_SEG == 0) {
+                // first instance of a backward segment: checkpoint this warp's compositing state (coalesced rows of 32)
+                float* ck = L.ckpt + ((size_t)(L.seg_offset[gt] + (unsigned)(c * WCHUNK / DM4D_SEG)) * (C + 2)) * 256 + warp * 32 + lane;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) ck[ch * 256] = Cacc[ch];
+                ck[C * 256] = D;
+                ck[(C + 1) * 256] = T;
+            }
             const float4* r = ring.wait(slot, c / WSTAGES);
             const int cnt = min(WCHUNK, n - c * WCHUNK);
             CellQueue q = cell_queue<TR::R4>(r, cnt, lane, warp, pm.half);
@@ -353,123 +339,58 @@ __global__ void __launch_bounds__(THREADS) render_forward_kernel(RasterLayout L,
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-// Recursive-halving reductions over the 16 lanes of a half-warp (xor distances 8, 4, 2, 1 never leave the half).
-// After the call lane `li` holds the half-warp total of ONE slot; `slot_of` gives that slot (or -1 for idle lanes).
-//
-// N = 16 slots: 8 + 4 + 2 + 1 = 15 shuffles, lane li ends with slot li.
-__device__ __forceinline__ float half_reduce_scatter16(float (&v)[16], int li) {
-    const bool b3 = li & 8, b2 = li & 4, b1 = li & 2, b0 = li & 1;
-    float w8[8], w4[4], w2[2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float send = b3 ? v[i] : v[i + 8], keep = b3 ? v[i + 8] : v[i];
-        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = b2 ? w8[i] : w8[i + 4], keep = b2 ? w8[i + 4] : w8[i];
-        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = b1 ? w4[i] : w4[i + 2], keep = b1 ? w4[i + 2] : w4[i];
-        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    const float send = b0 ? w2[0] : w2[1], keep = b0 ? w2[1] : w2[0];
-    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
-}
-// N = 10 slots (the 3-channel pass: 2 dmean2D, 3 dconic, dopacity, ddepth, 3 dfeatures): 10 -> 5 -> 3 -> 2 -> 1 with
-// 5 + 3 + 2 + 1 = 11 shuffles.  Lane li ends with slot 5*b3 + 3*b2 + (2*b1 + b0) when 2*b1 + b0 <= 2 and
-// 3*b2 + 2*b1 + b0 <= 4; the other six lanes of the half hold padding.
-__device__ __forceinline__ float half_reduce_scatter10(float (&v)[10], int li) {
-    const bool b3 = li & 8, b2 = li & 4, b1 = li & 2, b0 = li & 1;
-    float w[6], x[4], y[2];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const float send = b3 ? v[i] : v[i + 5], keep = b3 ? v[i + 5] : v[i];
-        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    w[5] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const float send = b2 ? w[i] : w[i + 3], keep = b2 ? w[i + 3] : w[i];
-        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    x[3] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = b1 ? x[i] : x[i + 2], keep = b1 ? x[i + 2] : x[i];
-        y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    const float send = b0 ? y[0] : y[1], keep = b0 ? y[1] : y[0];
-    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
-}
-__device__ __forceinline__ int slot_of10(int li) {
-    const int t = li & 3, u = ((li & 4) ? 3 : 0) + t;
-    return (t <= 2 && u <= 4) ? ((li & 8) ? 5 : 0) + u : -1;
+#ifndef DM4D_BWD_CHUNK
+#define DM4D_BWD_CHUNK 64      // instances per staged chunk of the backward (32: smaller ring, more resident warps, but +10 % time)
+#endif
+constexpr int BCHUNK = DM4D_BWD_CHUNK;
+static_assert(BCHUNK == 32 || BCHUNK == 64, "DM4D_BWD_CHUNK must be 32 or 64");
+static_assert(DM4D_SEG % 64 == 0, "segments are whole chunks of the forward and of the backward");
+
+// candidate queue of a 32-instance chunk: one ballot per cell
+template <int R4>
+__device__ __forceinline__ CellQueue cell_queue32(const float4* r, int cnt, int lane, int warp, int half) {
+    const unsigned int m0 = lane < cnt ? __float_as_uint(r[lane * R4 + 1].z) : 0u;
+    const int sh = 2 * warp;
+    const unsigned int a0 = __ballot_sync(0xffffffffu, (m0 >> sh) & 1u), b0 = __ballot_sync(0xffffffffu, (m0 >> (sh + 1)) & 1u);
+    CellQueue q;
+    q.lo = half ? b0 : a0;
+    q.hi = 0u;
+    return q;
 }
 
-#if DM4D_CELL_ROWS == 2
-// EXPERIMENTAL quarter-warp (8 lanes, xor distances 4, 2, 1) reductions: every lane ends with up to TWO slots.
-// N = 10: 10 -> 5 -> 3 -> 2 with 5 + 3 + 2 = 10 shuffles; lane li (bits b2 b1 b0) holds out[k], k = 0, 1, for slot
-// 5 b2 + 3 b1 + (2 b0 + k) when 2 b0 + k <= 2 and 3 b1 + 2 b0 + k <= 4 (quarter_slot10), else padding.
-__device__ __forceinline__ void quarter_reduce_scatter10(float (&v)[10], int li, float (&out)[2]) {
-    const bool b2 = li & 4, b1 = li & 2, b0 = li & 1;
-    float w[6], x[4];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const float send = b2 ? v[i] : v[i + 5], keep = b2 ? v[i + 5] : v[i];
-        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    w[5] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const float send = b1 ? w[i] : w[i + 3], keep = b1 ? w[i + 3] : w[i];
-        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    x[3] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = b0 ? x[i] : x[i + 2], keep = b0 ? x[i + 2] : x[i];
-        out[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-    }
+// Shared memory of one backward warp behind its record ring: the (h, w) rows of up to 2 x 16 (cell, instance) pairs,
+// the per-pixel loss gradients of the warp's two cells, and the instance slot of every pair.
+template <int C>
+struct BwdScratch {
+    static constexpr int SLOTS = 16;               // pairs per half-warp per batch
+    static constexpr int ROW = 34;                 // floats per pair: 16 pixels x (h, w) + 2 pad -> conflict-free 8-byte accesses
+    static constexpr int PC = C <= 3 ? 4 : 8;      // per-pixel constants: dL/dC[0..C), dL/dD (+ pad)
+    float hw[2 * SLOTS * ROW];
+    float pc[32 * PC];
+    int slot_j[2 * SLOTS];
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ int quarter_slot10(int li, int k) {
-    const int t = ((li & 1) ? 2 : 0) + k, u = ((li & 2) ? 3 : 0) + t;
-    return (t <= 2 && u <= 4) ? ((li & 4) ? 5 : 0) + u : -1;
-}
-// N = 16: 16 -> 8 -> 4 -> 2 with 8 + 4 + 2 = 14 shuffles; lane li holds slots 2 li and 2 li + 1.
-__device__ __forceinline__ void quarter_reduce_scatter16(float (&v)[16], int li, float (&out)[2]) {
-    const bool b2 = li & 4, b1 = li & 2, b0 = li & 1;
-    float w8[8], w4[4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float send = b2 ? v[i] : v[i + 8], keep = b2 ? v[i + 8] : v[i];
-        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = b1 ? w8[i] : w8[i + 4], keep = b1 ? w8[i + 4] : w8[i];
-        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = b0 ? w4[i] : w4[i + 2], keep = b0 ? w4[i + 2] : w4[i];
-        out[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-    }
-}
-#endif
 
 template <int C>
-__global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_kernel(RasterLayout L, const float* __restrict__ view_params,
+__global__ void __launch_bounds__(THREADS) render_backward_kernel(RasterLayout L, const float* __restrict__ view_params,
+                                                                   const float* __restrict__ out_color,
+                                                                   const float* __restrict__ out_depth,
                                                                    const float* __restrict__ out_alpha,
                                                                    const float* __restrict__ dL_dcolor,
                                                                    const float* __restrict__ dL_ddepth,
                                                                    const float* __restrict__ dL_dalpha_img) {
     using TR = RecTraits<C>;
+    using SC = BwdScratch<C>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
-    const int gt = (int)L.tile_order[blockIdx.x / PARTS];
+    // work item = (segment of a tile's instance list, 8x4 pixel block): one warp
+    const unsigned int seg = blockIdx.x / PARTS;
+    if (seg >= L.hdr->total_segs) return;           // also covers overflow (total_segs = 0)
+    const int gt = (int)L.seg_tile[seg];
+    const int ks = (int)(seg - L.seg_offset[gt]);   // segment index within the tile
     const int v = gt / L.tiles, t = gt - v * L.tiles;
     const int tile_x = t % L.gx, tile_y = t / L.gx;
     const int tid = threadIdx.x, lane = tid & 31, wl = tid >> 5;     // wl: warp within the CTA (ring slot)
@@ -482,160 +403,167 @@ __global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_
     const size_t pix = (size_t)py * L.W + px;
 
     const unsigned int beg = L.tile_offset[gt];
-    const int n = L.hdr->overflow ? 0 : (int)(L.tile_offset[gt + 1] - beg);
-    if (n == 0) return;
+    const int n = (int)(L.tile_offset[gt + 1] - beg);
+    const int m0 = ks * DM4D_SEG;                   // first instance of this segment
+    const int seg_end = m0 + DM4D_SEG;              // first instance of the next one
 
     const unsigned int last_contributor = inside ? L.n_contrib[(size_t)v * npix + pix] : 0u;
     unsigned int warp_last = last_contributor;      // last contributor over the warp's 32 pixels
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
-    if (warp_last == 0) return;                      // nothing composited in this block
-    const int nlive = min(n, (int)warp_last);        // this warp only needs instances in front of its last contributor
-    const int nchunks = (nlive + WCHUNK - 1) / WCHUNK;
+    if ((unsigned int)m0 >= warp_last) return;       // nothing composited by this block from here on
+    const int m1 = min(min(n, seg_end), (int)warp_last);
+    const int c0 = m0 / BCHUNK, nchunks = (m1 - m0 + BCHUNK - 1) / BCHUNK;
 
-    WarpRing<C> ring;
-    ring.init(smem_raw, wl, lane, L.stream + (size_t)beg * TR::REC, nlive);
-    // k-th chunk in processing order = chunk index nchunks-1-k (back to front)
+    WarpRing<C, BCHUNK> ring;
+    ring.init(smem_raw, wl, lane, L.stream + (size_t)beg * TR::REC, m1);
+    // k-th chunk in processing order = chunk c0 + nchunks-1-k (back to front)
     if (lane == 0)
-        for (int k = 0; k < min(WSTAGES, nchunks); ++k) ring.issue(nchunks - 1 - k, k);
+        for (int k = 0; k < min(WSTAGES, nchunks); ++k) ring.issue(c0 + nchunks - 1 - k, k);
+    SC& sc = *reinterpret_cast<SC*>(smem_raw + WarpRing<C, BCHUNK>::smem_bytes() + (size_t)wl * sizeof(SC));
 
     const float* vp = view_params + (size_t)v * DM4D_VIEW_STRIDE;
     float gC[C];
-    float bg_dot = 0.f;
+    float bg_dot = 0.f, F = 0.f;
+    const float T_final = inside ? 1.0f - out_alpha[(size_t)v * npix + pix] : 0.f;
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) {
         gC[ch] = inside ? dL_dcolor[((size_t)v * C + ch) * npix + pix] : 0.f;
-        bg_dot += vp[DM4D_VIEW_BG + ch] * gC[ch];
+        const float bgc = vp[DM4D_VIEW_BG + ch];
+        bg_dot += bgc * gC[ch];
+        // composited feature without the background term: out_color = sum_k w_k c_k + T_final bg
+        F += gC[ch] * (inside ? out_color[((size_t)v * C + ch) * npix + pix] - T_final * bgc : 0.f);
+        sc.pc[lane * SC::PC + ch] = gC[ch];
     }
     const float gD = (inside && dL_ddepth) ? dL_ddepth[(size_t)v * npix + pix] : 0.f;
     const float gA = (inside && dL_dalpha_img) ? dL_dalpha_img[(size_t)v * npix + pix] : 0.f;
-    const float T_final = inside ? 1.0f - out_alpha[(size_t)v * npix + pix] : 0.f;
-    float T = T_final;
-    float accum_rec[C], last_color[C];
+    sc.pc[lane * SC::PC + C] = gD;
+    if constexpr (C > 3) sc.pc[lane * SC::PC + C + 1] = 0.f;
+    if (inside) F += gD * out_depth[(size_t)v * npix + pix] + gA * (1.0f - T_final);
+
+    // State "behind" the segment.  Pixels whose contributors end inside it: (T_final, background), as in the replaced
+    // rasterizer.  Pixels that continue past seg_end: T from the next segment's checkpoint, Q = (what is composited
+    // behind the boundary, background included) / T — the totals come from the forward's output images.
+    float T = T_final, Q = bg_dot;
+    if (last_contributor > (unsigned int)seg_end) {
+        const float* ck = L.ckpt + ((size_t)(seg + 1) * (C + 2)) * 256 + warp * 32 + lane;
+        const float Tb = ck[(C + 1) * 256];
+        float Pb = gD * ck[C * 256] + gA * (1.0f - Tb);
 #pragma unroll
-    for (int ch = 0; ch < C; ++ch) { accum_rec[ch] = 0.f; last_color[ch] = 0.f; }
-    float accum_d = 0.f, last_depth = 0.f, accum_a = 0.f, last_alpha = 0.f;
-    const float ddelx_dx = 0.5f * (float)L.W, ddely_dy = 0.5f * (float)L.H;
+        for (int ch = 0; ch < C; ++ch) Pb += gC[ch] * ck[ch * 256];
+        T = Tb;
+        Q = (F + T_final * bg_dot - Pb) / Tb;
+    }
+    const float kx = 0.5f * (float)L.W, ky = 0.5f * (float)L.H;
     float* accum_view = L.accum + (size_t)v * L.P * TR::ACC;
-    // accumulator-row offset this lane adds its reduced slot to (rows: raster_internal.cuh); -1 = idle lane
-#if DM4D_CELL_ROWS == 4
-    int acc_off;
-    if constexpr (C <= 3) {
-        const int sl = slot_of10(pm.li);          // reduction slots 0..6 = row 0..6, slots 7..9 = features at row 8..10
-        acc_off = sl < 0 ? -1 : (sl < 7 ? sl : sl + 1);
-    } else {
-        acc_off = (pm.li != 7 && pm.li < 8 + C) ? pm.li : -1;
-    }
     const unsigned int half_lanes = 0xffffu << (pm.half * 16);
-#else
-    int acc_off2[2];                              // EXPERIMENTAL: two reduced slots per lane of a quarter-warp
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        if constexpr (C <= 3) {
-            const int sl = quarter_slot10(pm.li, k);
-            acc_off2[k] = sl < 0 ? -1 : (sl < 7 ? sl : sl + 1);
-        } else {
-            const int sl = 2 * pm.li + k;         // lane li of the 16 -> 8 -> 4 -> 2 halving holds slots 2 li, 2 li + 1
-            acc_off2[k] = (sl != 7 && sl < 8 + C) ? sl : -1;
-        }
-    }
-    const unsigned int half_lanes = 0xffu << (pm.half * 8);
-#endif
+    __syncwarp();
 
     for (int k = 0; k < nchunks; ++k) {
-        const int c = nchunks - 1 - k;
+        const int c = c0 + nchunks - 1 - k;
         const int sl = k % WSTAGES;
         const float4* r = ring.wait(sl, k / WSTAGES);
-        const int cnt = min(WCHUNK, nlive - c * WCHUNK);
-        CellQueue q = cell_queue<TR::R4>(r, cnt, lane, warp, pm.half);
+        const int cnt = min(BCHUNK, m1 - c * BCHUNK);
+        CellQueue q = BCHUNK == 64 ? cell_queue<TR::R4>(r, cnt, lane, warp, pm.half) : cell_queue32<TR::R4>(r, cnt, lane, warp, pm.half);
         while (__any_sync(0xffffffffu, !q.empty())) {
-            // next instance of this half-warp's queue, back to front (the two halves walk different instances)
-            const bool have = !q.empty();
-            const int j = have ? q.pop_back() : 0;
-            const unsigned int gi = (unsigned int)(c * WCHUNK + j);
-            const float4* rp = r + j * TR::R4;
-            bool valid = have && gi < last_contributor;
-            float4 a, b;
-            float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
-            if (valid) {
-                a = rp[0];
-                b = rp[1];
-                dx = a.x - pfx; dy = a.y - pfy;
-                const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-                valid = !(power > 0.0f);
-                if (valid) {
-                    G = gauss_exp(power);
-                    alpha = fminf(0.99f, b.y * G);
-                    valid = !(alpha < 1.0f / 255.0f);
-                }
-            }
-            const unsigned int vb = __ballot_sync(0xffffffffu, valid);
-            if (vb == 0u) continue;
-
-            // reduction slots: 0-1 dmean2D, 2-4 dconic, 5 dopacity, 6 ddepth, then the C feature gradients
-            // (3 channels: slots 7..9 of a 10-slot reduction; 6 channels: slots 8..13 of a 16-slot one, 7 unused)
-            constexpr int NS = C <= 3 ? 10 : 16;
-            constexpr int F0 = C <= 3 ? 7 : 8;
-            float gv[NS];
-#pragma unroll
-            for (int i = 0; i < NS; ++i) gv[i] = 0.f;
-            if (valid) {
-                const float inv_1ma = fast_rcp(1.0f - alpha);       // MUFU.RCP (1 ulp), shared by both uses below
-                T = T * inv_1ma;
-                const float w = alpha * T;
+            // ---- sweep 1: pixel-parallel, back to front, up to SLOTS instances per half-warp; straight-line code ------
+            int n_mine = 0;                           // pairs of this lane's half in the batch (uniform within the half)
+            // everything of one candidate that does not depend on the running (T, Q): two candidates are evaluated per
+            // step so their shared-memory loads, exponent and exp overlap; only the three-instruction (T, Q) update is serial
+            struct Cand { float G, al, sj; bool valid; int slot_val; };
+            auto eval = [&](bool have, int j) -> Cand {
+                const float4* rp = r + j * TR::R4;
+                const float4 a = rp[0];
+                const float4 b = rp[1];
                 float f[C], dep;
                 load_features<C>(rp, f, dep);
-                float dL_dalpha = 0.f;
+                const float dx = a.x - pfx, dy = a.y - pfy;
+                const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+                Cand o;
+                o.G = gauss_exp(fminf(power, 0.0f));
+                const float alpha = fminf(0.99f, b.y * o.G);
+                o.valid = have && (unsigned int)(c * BCHUNK + j) < last_contributor && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                o.al = o.valid ? alpha : 0.0f;                           // alpha = 0 leaves (T, Q) untouched
+                o.sj = gA + dep * gD;
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) {
-                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                    last_color[ch] = f[ch];
-                    dL_dalpha += (f[ch] - accum_rec[ch]) * gC[ch];
-                    gv[F0 + ch] = w * gC[ch];
+                for (int ch = 0; ch < C; ++ch) o.sj += f[ch] * gC[ch];
+                const unsigned int vb = __ballot_sync(0xffffffffu, o.valid);
+                o.slot_val = (have && (vb & half_lanes)) ? j : -1;
+                return o;
+            };
+            auto advance = [&](const Cand& cd, int it) {
+                T *= fast_rcp(1.0f - cd.al);                             // T_j (MUFU.RCP, 1 ulp)
+                const float d = cd.sj - Q;
+                const float hval = cd.valid ? cd.G * (T * d) : 0.0f;     // G dL/dalpha
+                Q += cd.al * d;                                          // Q_{j-1} = alpha s + (1 - alpha) Q
+                *reinterpret_cast<float2*>(&sc.hw[(pm.half * SC::SLOTS + it) * SC::ROW + 2 * pm.li]) = make_float2(hval, cd.al * T);
+                if (pm.li == 0) sc.slot_j[pm.half * SC::SLOTS + it] = cd.slot_val;
+            };
+            for (int it = 0; it < SC::SLOTS && __any_sync(0xffffffffu, !q.empty()); it += 2) {
+                const bool have0 = !q.empty();
+                const int j0 = have0 ? q.pop_back() : 0;                 // record 0 of the chunk is always readable
+                const bool have1 = !q.empty();
+                const int j1 = have1 ? q.pop_back() : 0;
+                const Cand ca = eval(have0, j0);
+                const Cand cb = eval(have1, j1);
+                advance(ca, it);
+                advance(cb, it + 1);
+                n_mine += (have0 ? 1 : 0) + (have1 ? 1 : 0);
+            }
+            const int n0 = __shfl_sync(0xffffffffu, n_mine, 0), n1 = __shfl_sync(0xffffffffu, n_mine, 16);
+            __syncwarp();
+            // ---- sweep 2: pair-parallel — lane p owns one (cell, instance) pair and sums its 16 pixels ----------------
+            if (lane < n0 + n1) {
+                const int h2 = lane < n0 ? 0 : 1, slot = lane < n0 ? lane : lane - n0;
+                const int j = sc.slot_j[h2 * SC::SLOTS + slot];
+                if (j >= 0) {
+                    const float4* rp = r + j * TR::R4;
+                    const float4 a = rp[0];
+                    const float4 b = rp[1];
+                    // pixel (i, jrow) of the cell sits at (ox + i, oy + jrow); offsets rounded once, exactly as in sweep 1
+                    const int ox = tile_x * DM4D_TILE + ((((warp & 1) << 1) | h2) << 2), oy = tile_y * DM4D_TILE + ((warp >> 1) << 2);
+                    float dxs[4], dys[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { dxs[i] = a.x - (float)(ox + i); dys[i] = a.y - (float)(oy + i); }
+                    const float* row = &sc.hw[(h2 * SC::SLOTS + slot) * SC::ROW];
+                    const float* pcs = &sc.pc[h2 * 16 * SC::PC];
+                    float S0 = 0.f, Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, Sd = 0.f;
+                    float Sf[C];
+#pragma unroll
+                    for (int ch = 0; ch < C; ++ch) Sf[ch] = 0.f;
+#pragma unroll
+                    for (int p = 0; p < 16; ++p) {
+                        const float2 hwv = *reinterpret_cast<const float2*>(row + 2 * p);
+                        const float dx = dxs[p & 3], dy = dys[p >> 2];
+                        const float tx = hwv.x * dx, ty = hwv.x * dy;
+                        S0 += hwv.x; Sx += tx; Sy += ty;
+                        Sxx += tx * dx; Sxy += tx * dy; Syy += ty * dy;
+                        if constexpr (C <= 3) {
+                            const float4 g4 = *reinterpret_cast<const float4*>(pcs + p * SC::PC);
+                            Sf[0] += hwv.y * g4.x; Sf[1] += hwv.y * g4.y; Sf[2] += hwv.y * g4.z; Sd += hwv.y * g4.w;
+                        } else {
+                            const float4 g4 = *reinterpret_cast<const float4*>(pcs + p * SC::PC);
+                            const float4 g5 = *reinterpret_cast<const float4*>(pcs + p * SC::PC + 4);
+                            Sf[0] += hwv.y * g4.x; Sf[1] += hwv.y * g4.y; Sf[2] += hwv.y * g4.z; Sf[3] += hwv.y * g4.w;
+                            Sf[4] += hwv.y * g5.x; Sf[5] += hwv.y * g5.y; Sd += hwv.y * g5.z;
+                        }
+                    }
+                    // accumulator row: [0..1] dmean2D, [2..4] dconic (x, y(half), z), [5] dopacity, [6] ddepth, [7] pad, [8..] dfeatures
+                    const float o = b.y;
+                    float* acc = accum_view + (size_t)__float_as_int(b.w) * TR::ACC;
+                    red_add_v4(acc, -o * kx * (a.z * Sx + a.w * Sy), -o * ky * (b.x * Sy + a.w * Sx), -0.5f * o * Sxx, -0.5f * o * Sxy);
+                    red_add_v4(acc + 4, -0.5f * o * Syy, S0, Sd, 0.f);
+                    if constexpr (C <= 3) {
+                        red_add_v4(acc + 8, Sf[0], Sf[1], Sf[2], 0.f);
+                    } else {
+                        red_add_v4(acc + 8, Sf[0], Sf[1], Sf[2], Sf[3]);
+                        red_add_v4(acc + 12, Sf[4], Sf[5], 0.f, 0.f);
+                    }
                 }
-                accum_d = last_alpha * last_depth + (1.f - last_alpha) * accum_d;
-                last_depth = dep;
-                dL_dalpha += (dep - accum_d) * gD;
-                gv[6] = w * gD;
-                accum_a = last_alpha + (1.f - last_alpha) * accum_a;
-                dL_dalpha += (1.f - accum_a) * gA;
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final * inv_1ma) * bg_dot;
-                const float dL_dG = b.y * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * a.z - gdy * a.w;
-                const float dG_ddely = -gdy * b.x - gdx * a.w;
-                gv[0] = dL_dG * dG_ddelx * ddelx_dx;
-                gv[1] = dL_dG * dG_ddely * ddely_dy;
-                const float hx = -0.5f * dL_dG * gdx, hy = -0.5f * dL_dG * gdy;   // shared factors of the conic terms
-                gv[2] = hx * dx;
-                gv[3] = hx * dy;
-                gv[4] = hy * dy;
-                gv[5] = G * dL_dalpha;
             }
-#if DM4D_CELL_ROWS == 4
-            float tot;
-            if constexpr (C <= 3) tot = half_reduce_scatter10(gv, pm.li);
-            else tot = half_reduce_scatter16(gv, pm.li);
-            // one coalesced reduction per (half-warp, instance) into the instance's accumulator row
-            if (acc_off >= 0 && (vb & half_lanes)) {
-                const int id = __float_as_int(rp[1].w);
-                atomicAdd(accum_view + (size_t)id * TR::ACC + acc_off, tot);
-            }
-#else
-            float tot2[2];
-            if constexpr (C <= 3) quarter_reduce_scatter10(gv, pm.li, tot2);
-            else quarter_reduce_scatter16(gv, pm.li, tot2);
-            if (vb & half_lanes) {                // this quarter-warp's instance had a contributing lane
-                float* row = accum_view + (size_t)__float_as_int(rp[1].w) * TR::ACC;
-                if (acc_off2[0] >= 0) atomicAdd(row + acc_off2[0], tot2[0]);
-                if (acc_off2[1] >= 0) atomicAdd(row + acc_off2[1], tot2[1]);
-            }
-#endif
+            __syncwarp();
         }
-        __syncwarp();
-        if (lane == 0 && k + WSTAGES < nchunks) ring.issue(nchunks - 1 - (k + WSTAGES), sl);
+        if (lane == 0 && k + WSTAGES < nchunks) ring.issue(c0 + nchunks - 1 - (k + WSTAGES), sl);
     }
 }
 
@@ -658,9 +586,9 @@ int launch_fwd_t(const dm4d_raster_desc* d, const RasterLayout& L, float* out_co
 }
 
 template <int C>
-int launch_bwd_t(const dm4d_raster_desc* d, const RasterLayout& L, const float* out_alpha, const float* dL_dcolor,
-                 const float* dL_ddepth, const float* dL_dalpha, cudaStream_t s) {
-    const size_t smem = WarpRing<C>::smem_bytes();
+int launch_bwd_t(const dm4d_raster_desc* d, const RasterLayout& L, const float* out_color, const float* out_depth,
+                 const float* out_alpha, const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, cudaStream_t s) {
+    const size_t smem = WarpRing<C, BCHUNK>::smem_bytes() + (size_t)WARPS * sizeof(BwdScratch<C>);
     static bool configured = false;
     if (!configured) {
         DM4D_CUDA_CHECK(cudaFuncSetAttribute(render_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -669,8 +597,9 @@ int launch_bwd_t(const dm4d_raster_desc* d, const RasterLayout& L, const float* 
     DM4D_CUDA_CHECK(cudaMemsetAsync(L.accum, 0, (size_t)L.n_views * L.P * L.acc * sizeof(float), s));
     {
         KernelTimer kt(DM4D_K_RENDER_BWD, s);
-        render_backward_kernel<C><<<(unsigned)(L.n_views * L.tiles * PARTS), THREADS, smem, s>>>(L, d->view_params, out_alpha,
-                                                                                         dL_dcolor, dL_ddepth, dL_dalpha);
+        // one CTA group per POSSIBLE segment (host-side bound); CTAs past the device-side segment count exit at once
+        render_backward_kernel<C><<<(unsigned)(L.seg_cap * PARTS), THREADS, smem, s>>>(L, d->view_params, out_color, out_depth, out_alpha,
+                                                                               dL_dcolor, dL_ddepth, dL_dalpha);
     }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
@@ -685,9 +614,10 @@ int launch_render_forward(const dm4d_raster_desc* d, const RasterLayout& L, floa
                            : launch_fwd_t<6>(d, L, out_color, out_depth, out_alpha, s);
 }
 
-int launch_render_backward(const dm4d_raster_desc* d, const RasterLayout& L, const float* out_alpha,
-                           const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, cudaStream_t s) {
+int launch_render_backward(const dm4d_raster_desc* d, const RasterLayout& L, const float* out_color, const float* out_depth,
+                           const float* out_alpha, const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                           cudaStream_t s) {
     if (L.n_views * L.tiles == 0) return DM4D_OK;
-    return L.channels <= 3 ? launch_bwd_t<3>(d, L, out_alpha, dL_dcolor, dL_ddepth, dL_dalpha, s)
-                           : launch_bwd_t<6>(d, L, out_alpha, dL_dcolor, dL_ddepth, dL_dalpha, s);
+    return L.channels <= 3 ? launch_bwd_t<3>(d, L, out_color, out_depth, out_alpha, dL_dcolor, dL_ddepth, dL_dalpha, s)
+                           : launch_bwd_t<6>(d, L, out_color, out_depth, out_alpha, dL_dcolor, dL_ddepth, dL_dalpha, s);
 }

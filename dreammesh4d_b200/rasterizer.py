@@ -93,7 +93,7 @@ class RasterState:
     def __init__(self, desc: RasterDesc, keep: list, capacity: int):
         self.desc, self.keep, self.capacity = desc, keep, capacity
         self.radii: Optional[torch.Tensor] = None
-        self.alpha_version = 0
+        self.alpha_version = (0, 0, 0)
         self.pending = None          # deferred overflow verification of a speculative capacity (CapacityBook)
         self.overflowed = False
 
@@ -220,11 +220,11 @@ class _RasterizeBatch(torch.autograd.Function):
             check(l.dm4d_raster_forward(ctypes.byref(d), ptr(color), ptr(depth), ptr(alpha), ptr(radii), stream),
                   "dm4d_raster_forward")
 
-        # alpha.detach(): same storage and version counter, but no reference back to this node (no ctx <-> output cycle,
+        # output.detach(): same storage and version counter, but no reference back to this node (no ctx <-> output cycle,
         # so the workspaces are released by reference counting, not by the cyclic GC)
-        state = RasterState(d, [m, sc, ro, op, co, c2, vp, geom, bin_, img, alpha.detach()], capacity)
+        state = RasterState(d, [m, sc, ro, op, co, c2, vp, geom, bin_, img, alpha.detach(), color.detach(), depth.detach()], capacity)
         state.radii = radii
-        state.alpha_version = alpha._version      # the backward reads T_final = 1 - alpha from this very tensor
+        state.alpha_version = (alpha._version, color._version, depth._version)   # the backward reads these very images
         ctx.state = state
         ctx.workspace = workspace
         ctx.shapes = (means3D.shape, scales.shape, rotations.shape, opacities.shape, colors.shape,
@@ -242,11 +242,11 @@ class _RasterizeBatch(torch.autograd.Function):
         if st.pending is not None:
             st.pending.resolve(st)               # the header copy finished long ago: no stall
         d = st.desc
-        m, sc, ro, op, co, c2, vp, geom, bin_, img, alpha = st.keep
-        if alpha._version != st.alpha_version:
-            raise RuntimeError("the alpha image returned by the rasterizer was modified in place before backward(); the "
-                               "backward reads the final transmittance from it (as the replaced rasterizer does) — "
-                               "clone it before editing")
+        m, sc, ro, op, co, c2, vp, geom, bin_, img, alpha, color, depth = st.keep
+        if (alpha._version, color._version, depth._version) != st.alpha_version:
+            raise RuntimeError("an image returned by the rasterizer was modified in place before backward(); the backward "
+                               "reads the final transmittance and the composited totals from the forward's outputs (the "
+                               "replaced rasterizer reads alpha the same way) — clone before editing")
         dev = m.device
         stream = torch.cuda.current_stream().cuda_stream
         _, _, _, wb = (ctypes.c_uint64(0) for _ in range(4))
@@ -270,7 +270,7 @@ class _RasterizeBatch(torch.autograd.Function):
         d_rots = torch.empty_like(ro) if need[4] else None
         d_colors = torch.empty_like(co) if need[5] else None
         d_colors2 = torch.empty_like(c2) if (c2 is not None and need[6]) else None
-        check(l.dm4d_raster_backward(ctypes.byref(d), ptr(alpha), ptr(gC), ptr(gD), ptr(gA), ptr(d_means3D),
+        check(l.dm4d_raster_backward(ctypes.byref(d), ptr(color), ptr(depth), ptr(alpha), ptr(gC), ptr(gD), ptr(gA), ptr(d_means3D),
                                      ptr(d_means2D), ptr(d_colors), ptr(d_colors2), ptr(d_opac), ptr(d_scales),
                                      ptr(d_rots), stream), "dm4d_raster_backward")
         sh = ctx.shapes

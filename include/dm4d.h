@@ -87,7 +87,7 @@ typedef struct dm4d_raster_desc {
     const float* colors2;   int64_t colors2_stride;     /* [., P, 3] channels 3..5 (NULL if channels==3) */
     const float* view_params;                           /* [n_views, DM4D_VIEW_STRIDE] */
     void* geom; uint64_t geom_bytes;                    /* per-(view,Gaussian) projected state */
-    void* bin;  uint64_t bin_bytes;                     /* tile counts/offsets, keys, sorted instance stream */
+    void* bin;  uint64_t bin_bytes;                     /* tile / segment tables, keys, sorted instance stream, forward checkpoints */
     void* img;  uint64_t img_bytes;                     /* per-pixel n_contrib */
     void* bwd;  uint64_t bwd_bytes;                     /* backward accumulators (may be NULL for forward) */
     int64_t bin_capacity;                               /* instance capacity the bin workspace was sized for */
@@ -126,7 +126,7 @@ int dm4d_raster_render_features(const dm4d_raster_desc* planned, const dm4d_rast
                                 float* out_depth, float* out_alpha, void* stream);
 
 /* Status header: the first 16 bytes of the `bin` workspace are
- *     struct { uint64_t num_rendered; uint32_t overflow; uint32_t pad; }
+ *     struct { uint64_t num_rendered; uint32_t overflow; uint32_t n_segments; }
  * written by the plan phase on the device.  A caller that must not synchronise (CUDA-graph replay, a training loop)
  * reads or accumulates the flag with its own device-side ops and polls it every N steps; dm4d_raster_status is the
  * synchronous convenience form.  When `overflow` is 1 the render and backward kernels treat every tile as empty
@@ -135,16 +135,17 @@ int dm4d_raster_render_features(const dm4d_raster_desc* planned, const dm4d_rast
 int dm4d_raster_status(const dm4d_raster_desc* d, int64_t* num_rendered_host, int32_t* overflow_host,
                        void* stream);
 
-/* Backward of dm4d_raster_forward for the same desc/workspaces; `out_alpha` is the forward's alpha
- * output (the replaced rasterizer saves it the same way).  dL_ddepth / dL_dalpha may be
- * NULL (zero).  Gradient outputs have the shape of the matching input ([n_sets or 1, P, k]) and
- * are fully overwritten (summed over the views that used each set entry);
- * dL_dmeans2D is [n_views, P, 3] (z = 0, NDC-scaled as in the replaced rasterizer).
+/* Backward of dm4d_raster_forward (or dm4d_raster_render_features) for the same desc/workspaces.  `out_color`,
+ * `out_depth`, `out_alpha` are the forward's output images (the replaced rasterizer saves alpha the same way; the
+ * colour and depth images let each pixel start from the total of its composited sum, so the backward runs front to
+ * back in independent segments — see csrc/raster_render.cu).  dL_ddepth / dL_dalpha may be NULL (zero).  Gradient
+ * outputs have the shape of the matching input ([n_sets or 1, P, k]) and are fully overwritten (summed over the views
+ * that used each set entry); dL_dmeans2D is [n_views, P, 3] (z = 0, NDC-scaled as in the replaced rasterizer).
  * Any output pointer may be NULL to skip it. */
-int dm4d_raster_backward(const dm4d_raster_desc* d, const float* out_alpha, const float* dL_dcolor,
-                         const float* dL_ddepth, const float* dL_dalpha, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcolors,
-                         float* dL_dcolors2, float* dL_dopacities, float* dL_dscales, float* dL_drotations,
-                         void* stream);
+int dm4d_raster_backward(const dm4d_raster_desc* d, const float* out_color, const float* out_depth, const float* out_alpha,
+                         const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha, float* dL_dmeans3D,
+                         float* dL_dmeans2D, float* dL_dcolors, float* dL_dcolors2, float* dL_dopacities,
+                         float* dL_dscales, float* dL_drotations, void* stream);
 
 /* Test/inspection helper: copies the integer binning state of one view to device arrays:
  * ranges [tiles, 2] (uint32, relative to the view's first instance), point_list [R_view] (uint32
