@@ -87,6 +87,7 @@ SIGNATURES = {
     "dm4d_hexplane_forward": (ctypes.c_int, [POINTER(HexplaneDesc), c_void_p, c_void_p]),
     "dm4d_hexplane_backward": (ctypes.c_int, [POINTER(HexplaneDesc), c_void_p, POINTER(c_void_p), c_void_p]),
     "dm4d_graph_knn": (ctypes.c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "dm4d_graph_geodesic_sweep": (ctypes.c_int, [c_int32, c_int32] + [c_void_p] * 9),
     "dm4d_groupnorm_nhwc_forward": (ctypes.c_int, [c_void_p] * 4 + [c_int32] * 4 + [ctypes.c_float] + [c_int32] * 2 + [c_void_p] * 4),
     "dm4d_groupnorm_nhwc_backward": (ctypes.c_int, [c_void_p] * 5 + [c_int32] * 4 + [ctypes.c_float] + [c_int32] * 2 + [c_void_p] * 4),
     "dm4d_profile_enable": (ctypes.c_int, [ctypes.c_int]),

@@ -13,6 +13,7 @@
 //                     normals
 // Quaternion algebra follows pypose's SO3 semantics (xyzw).  Backward = exact
 // Euclidean gradients of the forward formulas.
+#include <algorithm>
 #include "raster_internal.cuh"
 
 namespace {
@@ -182,11 +183,11 @@ struct SkinBwdK {
     float* dn_trans; float* dn_rot; float* dn_scale; float* dn_opac;
 };
 
-__global__ void __launch_bounds__(DM4D_BLOCK) skin_vertex_backward_kernel(SkinBwdK a) {
+// Backward of one (timestamp, vertex): adds its contributions to the four node-gradient tables of timestamp t
+// (tT [M,3], tQ [M,4], tS [M,9], tO [M]) — global memory, or a per-CTA copy in shared memory.
+__device__ __forceinline__ void vertex_backward(const SkinBwdK& a, int t, int v, float* tT, float* tQ, float* tS, float* tO) {
     const dm4d_skin_desc& d = a.d;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)d.n_t * d.V) return;
-    const int t = (int)(idx / d.V), v = (int)(idx - (long long)t * d.V);
+    const long long idx = (long long)t * d.V + v;
     const f3 x = ld3(d.rest_verts + (size_t)v * 3);
     const f3 gx = ld3(a.dverts + (size_t)idx * 3);
     const float4 gr = ldq(a.dvert_rot + (size_t)idx * 4);
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK) skin_vertex_backward_kernel(SkinBw
             // so use the exact adjoint of p -> p + 2w(v x p) + 2 v x (v x p): g + 2w (g x v) + 2 (v x (v x g))
             const f3 vq = vec(q);
             const f3 dy = g + 2.f * (q.w * cross(g, vq) + cross(vq, cross(vq, g)));
-            float* dS = a.dn_scale + base * 9;
+            float* dS = tS + (size_t)n * 9;
             atomicAdd(dS + 0, dy.x * x.x); atomicAdd(dS + 1, dy.x * x.y); atomicAdd(dS + 2, dy.x * x.z);
             atomicAdd(dS + 3, dy.y * x.x); atomicAdd(dS + 4, dy.y * x.y); atomicAdd(dS + 5, dy.y * x.z);
             atomicAdd(dS + 6, dy.z * x.x); atomicAdd(dS + 7, dy.z * x.y); atomicAdd(dS + 8, dy.z * x.z);
@@ -264,11 +265,47 @@ __global__ void __launch_bounds__(DM4D_BLOCK) skin_vertex_backward_kernel(SkinBw
             dtr = dtr + 0.5f * vec(dth);
             dq = dq + inv * (dqn + (-dot4(qn, dqn)) * qn);
         }
-        if (d.method == 2) atomicAdd(a.dn_opac + base, w * dlam_raw);
-        float* dT = a.dn_trans + base * 3;
+        if (d.method == 2) atomicAdd(tO + n, w * dlam_raw);
+        float* dT = tT + (size_t)n * 3;
         atomicAdd(dT + 0, dtr.x); atomicAdd(dT + 1, dtr.y); atomicAdd(dT + 2, dtr.z);
-        float* dQ = a.dn_rot + base * 4;
+        float* dQ = tQ + (size_t)n * 4;
         atomicAdd(dQ + 0, dq.x); atomicAdd(dQ + 1, dq.y); atomicAdd(dQ + 2, dq.z); atomicAdd(dQ + 3, dq.w);
+    }
+}
+
+// Fallback for node tables that do not fit in shared memory: 17 global atomics per (t, vertex, neighbour).
+__global__ void __launch_bounds__(DM4D_BLOCK) skin_vertex_backward_kernel(SkinBwdK a) {
+    const dm4d_skin_desc& d = a.d;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)d.n_t * d.V) return;
+    const int t = (int)(idx / d.V), v = (int)(idx - (long long)t * d.V);
+    const size_t tb = (size_t)t * d.M;
+    vertex_backward(a, t, v, a.dn_trans + tb * 3, a.dn_rot + tb * 4, a.dn_scale + tb * 9, a.dn_opac + tb);
+}
+
+// Node-gradient tables of ONE timestamp accumulated in shared memory (M x 17 floats: 68 KB at M = 1000): a vertex adds
+// to its K nodes with shared-memory atomics — a block's vertices are mesh-neighbours and share a few dozen nodes, which
+// in global memory meant 13.6 M atomics on 8.7 k addresses at C5 (0.38 ms of the 0.45 ms skinning fwd+bwd) — and the
+// CTA flushes its non-zero entries once.  grid = (CTAs per timestamp, n_t); every CTA walks its vertices grid-stride.
+__global__ void __launch_bounds__(DM4D_BLOCK) skin_vertex_backward_smem_kernel(SkinBwdK a) {
+    extern __shared__ float tab[];
+    const dm4d_skin_desc& d = a.d;
+    const int M = d.M, t = blockIdx.y;
+    float* tT = tab; float* tQ = tT + (size_t)M * 3; float* tS = tQ + (size_t)M * 4; float* tO = tS + (size_t)M * 9;
+    for (int i = threadIdx.x; i < M * 17; i += blockDim.x) tab[i] = 0.f;
+    __syncthreads();
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < d.V; v += gridDim.x * blockDim.x) vertex_backward(a, t, v, tT, tQ, tS, tO);
+    __syncthreads();
+    const size_t tb = (size_t)t * M;
+    for (int i = threadIdx.x; i < M * 17; i += blockDim.x) {
+        const float val = tab[i];
+        if (val == 0.f) continue;
+        float* dst;
+        if (i < M * 3) dst = a.dn_trans + tb * 3 + i;
+        else if (i < M * 7) dst = a.dn_rot + tb * 4 + (i - M * 3);
+        else if (i < M * 16) dst = a.dn_scale + tb * 9 + (i - M * 7);
+        else dst = a.dn_opac + tb + (i - M * 16);
+        atomicAdd(dst, val);
     }
 }
 
@@ -578,7 +615,22 @@ extern "C" int dm4d_skin_backward(const dm4d_skin_desc* d, const float* verts, c
         skin_gaussian_backward_kernel<<<(unsigned)((nf + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(a);
     }
     DM4D_CUDA_CHECK(cudaGetLastError());
-    { KernelTimer kt(DM4D_K_SKIN_VERT_BWD, s); skin_vertex_backward_kernel<<<(unsigned)((nv + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(a); }
+    {
+        KernelTimer kt(DM4D_K_SKIN_VERT_BWD, s);
+        const size_t tab_bytes = (size_t)d->M * 17 * sizeof(float);
+        if (tab_bytes <= 200 * 1024) {
+            static bool configured = false;
+            if (!configured) {
+                DM4D_CUDA_CHECK(cudaFuncSetAttribute(skin_vertex_backward_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                configured = true;
+            }
+            const int resident = 148 * (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (tab_bytes + 1024)));
+            const int per_t = std::max(1, std::min((d->V + DM4D_BLOCK - 1) / DM4D_BLOCK, std::max(4, resident / d->n_t)));
+            skin_vertex_backward_smem_kernel<<<dim3((unsigned)per_t, (unsigned)d->n_t), DM4D_BLOCK, tab_bytes, s>>>(a);
+        } else {
+            skin_vertex_backward_kernel<<<(unsigned)((nv + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(a);
+        }
+    }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }

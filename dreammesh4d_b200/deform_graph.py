@@ -12,8 +12,15 @@ Modes
   (:783-789, 857-861).
 * ``"falloff"``  — Euclidean neighbour sets with the weight formula of the geodesic mode,
   ``(1 - d_k / d_{K+1})^2`` row-normalised (:845, 859-861): the synthetic benchmark graphs.
-The geodesic mode itself needs potpourri3d's heat-method solver (un-vendored, sparse Cholesky per mesh) and is not
-built.  Control nodes are an input (the reference samples them with Open3D's RNG, or takes ``xyz_nodes``).
+* ``"geodisc"``  — the YAML's mode (configs/sugar_dynamic_dg.yaml:85): the K nearest nodes by GEODESIC distance, weights
+  ``(1 - d_k / d_{K+1})^2`` of the EUCLIDEAN vertex-node distances, row-normalised (:791-849).  The reference runs one
+  heat-method solve per vertex (potpourri3d, un-vendored; minutes at V = 50k); here a multi-source label-correcting
+  propagation along the mesh edges on the GPU (``dm4d_graph_geodesic_sweep``, ~20 sweeps) gives the exact K-nearest
+  sets in the edge metric.  Edge-path lengths over-estimate the smoothed heat-method geodesics by a mesh-dependent
+  few percent; only the neighbour SELECTION depends on them.
+Control nodes: ``sample_surface_points`` draws them area-uniformly on the mesh like Open3D's
+``sample_points_uniformly`` (:753; a different RNG — the reference's own graphs are not reproducible across runs
+either), or pass ``xyz_nodes``.
 """
 from __future__ import annotations
 
@@ -36,8 +43,70 @@ def knn_nodes(queries: torch.Tensor, nodes: torch.Tensor, k: int):
     return idx, d2
 
 
+def sample_surface_points(verts: torch.Tensor, faces: torch.Tensor, n: int, seed: int = 0) -> torch.Tensor:
+    """``n`` points drawn uniformly w.r.t. area on the mesh surface (Open3D ``sample_points_uniformly`` semantics:
+    triangle ~ area, barycentric (1 - sqrt(r1), sqrt(r1)(1 - r2), sqrt(r1) r2))."""
+    g = torch.Generator().manual_seed(seed)
+    fv = verts.detach().cpu().double()[faces.detach().cpu().long()]
+    area = torch.cross(fv[:, 1] - fv[:, 0], fv[:, 2] - fv[:, 0], dim=-1).norm(dim=-1)
+    tri = torch.multinomial(area / area.sum(), n, replacement=True, generator=g)
+    r1, r2 = torch.rand(n, generator=g, dtype=torch.float64).sqrt(), torch.rand(n, generator=g, dtype=torch.float64)
+    b = torch.stack([1 - r1, r1 * (1 - r2), r1 * r2], dim=-1)
+    return (fv[tri] * b[..., None]).sum(dim=1).float().to(verts.device)
+
+
+def mesh_edge_csr(verts: torch.Tensor, faces: torch.Tensor):
+    """Undirected edge graph of the mesh as CSR over vertices: (row_ptr [V+1] int32, col [E] int32, length [E] fp32)."""
+    V = verts.shape[0]
+    f = faces.long()
+    i = torch.cat([f[:, 0], f[:, 1], f[:, 2], f[:, 1], f[:, 2], f[:, 0]])
+    j = torch.cat([f[:, 1], f[:, 2], f[:, 0], f[:, 0], f[:, 1], f[:, 2]])
+    key = torch.unique(i * V + j)                      # sorted by row, then column
+    rows, cols = key // V, key % V
+    row_ptr = torch.zeros(V + 1, dtype=torch.int64, device=verts.device)
+    row_ptr[1:] = torch.cumsum(torch.bincount(rows, minlength=V), 0)
+    length = (verts[rows] - verts[cols]).norm(dim=-1)
+    return row_ptr.int().contiguous(), cols.int().contiguous(), length.float().contiguous()
+
+
+def geodesic_knn_nodes(verts: torch.Tensor, faces: torch.Tensor, node_xyz: torch.Tensor, k: int, max_sweeps: int = 4096):
+    """(idx [V,k] int32, dist [V,k]) of the k nearest control nodes of every vertex along the mesh edges; a node enters
+    the mesh at its nearest vertex (dynamic_sugar.py:809-815).  Start-up code: polls one flag per sweep."""
+    if verts.device.type != "cuda":
+        raise _lib.Dm4dError("dreammesh4d_b200 graph construction needs CUDA tensors (there is no CPU path)")
+    verts = verts.detach().float().contiguous()
+    V, M = verts.shape[0], node_xyz.shape[0]
+    row_ptr, col, length = mesh_edge_csr(verts, faces)
+    entry, _ = knn_nodes(node_xyz, verts, 1)                                  # nearest mesh vertex of every node
+    entry = entry[:, 0].long()
+    dev = verts.device
+    dist = torch.full((V, k), float("inf"), device=dev)
+    node = torch.full((V, k), -1, dtype=torch.int32, device=dev)
+    # several nodes may enter at the same vertex: rank them inside their vertex group, lowest node index first
+    order = torch.argsort(entry * M + torch.arange(M, device=dev))
+    e_sorted = entry[order]
+    first = torch.ones(M, dtype=torch.bool, device=dev)
+    first[1:] = e_sorted[1:] != e_sorted[:-1]
+    start = torch.cummax(torch.where(first, torch.arange(M, device=dev), torch.zeros(M, dtype=torch.long, device=dev)), 0)[0]
+    rank = torch.arange(M, device=dev) - start
+    keep = rank < k
+    dist[e_sorted[keep], rank[keep]] = 0.0
+    node[e_sorted[keep], rank[keep]] = order[keep].int()
+    dist2, node2 = torch.empty_like(dist), torch.empty_like(node)
+    changed = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(max_sweeps):
+        changed.zero_()
+        check(_lib.lib().dm4d_graph_geodesic_sweep(V, k, ptr(row_ptr), ptr(col), ptr(length), ptr(dist), ptr(node), ptr(dist2),
+                                                   ptr(node2), ptr(changed), stream), "dm4d_graph_geodesic_sweep")
+        dist, dist2, node, node2 = dist2, dist, node2, node
+        if int(changed.item()) == 0:
+            break
+    return node, dist
+
+
 def build_deformation_graph(verts: torch.Tensor, node_xyz: torch.Tensor, nodes_connectivity: int = 6,
-                            mode: str = "eucdisc"):
+                            mode: str = "eucdisc", faces: torch.Tensor = None):
     """Returns ``(DeformGraph, connectivity [M,K] long)`` on the device of ``verts``."""
     K = nodes_connectivity
     if mode == "eucdisc":
@@ -48,8 +117,17 @@ def build_deformation_graph(verts: torch.Tensor, node_xyz: torch.Tensor, nodes_c
         d = d2.sqrt()
         w = (1.0 - d[:, :K] / d[:, K:K + 1].clamp_min(1e-12)) ** 2
         idx = idx[:, :K]
+    elif mode == "geodisc":
+        if faces is None:
+            raise ValueError("mode 'geodisc' needs the mesh faces")
+        idx, _ = geodesic_knn_nodes(verts, faces, node_xyz, K + 1)
+        if bool((idx < 0).any()):
+            raise ValueError("geodisc: some vertices reach fewer than K+1 control nodes along the mesh (disconnected mesh?)")
+        d = (verts[:, None, :] - node_xyz[idx.long()]).norm(dim=-1)            # Euclidean, as the reference (:836-838)
+        w = (1.0 - d[:, :K] / d[:, K:K + 1]) ** 2
+        idx = idx[:, :K]
     else:
-        raise ValueError("mode must be 'eucdisc' or 'falloff' (the geodesic mode needs potpourri3d and is not built)")
+        raise ValueError("mode must be 'eucdisc', 'geodisc' or 'falloff'")
     w = w / w.sum(dim=-1, keepdim=True).clamp_min(1e-12) if mode == "falloff" else w / w.sum(dim=-1, keepdim=True)
     conn, _ = knn_nodes(node_xyz, node_xyz, K + 1)
     return DeformGraph(node_xyz.float(), idx.long(), w.float()), conn[:, 1:].long()

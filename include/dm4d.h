@@ -284,6 +284,15 @@ int dm4d_hexplane_backward(const dm4d_hexplane_desc* d, const float* dL_dfeature
 int dm4d_graph_knn(const float* queries, int32_t n_queries, const float* nodes, int32_t n_nodes, int32_t k,
                    int32_t* idx, float* sqdist, void* stream);
 
+/* One Jacobi sweep of the geodesic K-nearest-node propagation (deformation-graph mode "geodisc", replaces the per-vertex
+ * heat-method solves of custom/threestudio-dreammesh4d/geometry/dynamic_sugar.py:791-849).  Mesh as CSR over vertices
+ * (row_ptr [V+1], col [E], edge_len [E]); labels dist/node [V,k] ascending by (distance, node), node = -1 / dist = +inf
+ * for empty slots.  Initialise the labels of every node's nearest vertex with (0, node); call with swapped in/out
+ * buffers until `*changed` (device int32, zeroed by the caller before each sweep) stays 0.  1 <= k <= 17. */
+int dm4d_graph_geodesic_sweep(int32_t V, int32_t k, const int32_t* row_ptr, const int32_t* col, const float* edge_len,
+                              const float* dist_in, const int32_t* node_in, float* dist_out, int32_t* node_out,
+                              int32_t* changed, void* stream);
+
 /* ---- channels-last GroupNorm (+ channel bias in front, + SiLU behind) for the Zero123 networks of the SDS step --------
  * (SURVEY.md §8 row A9).  Replaces, between the tensor-core convolutions that stay library calls, the
  * ``normalization(ch) -> SiLU`` pairs of ResBlock (extern/ldm_zero123/modules/diffusionmodules/openaimodel.py:210-214,

@@ -59,3 +59,45 @@ def test_falloff_mode_bench_graphs():
     same = (graph.nbr_idx.cpu() == ref.nbr_idx).all(dim=1)
     assert same.float().mean() > 0.97
     assert (graph.nbr_w.cpu()[same] - ref.nbr_w[same]).abs().max() < 1e-3
+
+
+def test_geodesic_oracle_known_answer_on_a_strip():
+    """A strip of quads folded back onto itself: its two ends are 0.15 apart in space but a whole strip length apart
+    along the surface — the case the geodesic mode exists for (limbs close in space, far along the mesh)."""
+    n = 12
+    i = np.arange(n)
+    x = np.where(i < n // 2, i, n - 1 - i) * 0.3
+    y = np.where(i < n // 2, 0.0, 0.15)
+    rail = np.stack([x, y, np.zeros(n)], 1)
+    verts = np.concatenate([rail, rail + np.array([0, 0, 0.3])]).astype(np.float32)
+    faces = np.array([[k, k + 1, n + k] for k in range(n - 1)] + [[k + 1, n + k + 1, n + k] for k in range(n - 1)])
+    nodes = verts[[0, n - 1]]                                             # the two ends of the strip
+    gi, gd = GO.geodesic_knn(verts, faces, nodes, 2)
+    _, ed2 = GO.knn(verts, nodes, 2)
+    assert gi[0].tolist() == [0, 1] and gi[n - 1].tolist() == [1, 0]
+    assert abs(np.sqrt(ed2[0, 1]) - 0.15) < 1e-6                          # straight through space ...
+    walk = 0.3 * (n - 2) + 0.15                                           # ... versus along the rail (10 steps + the fold)
+    assert abs(gd[0, 1] - walk) < 1e-5 and abs(gd[n - 1, 1] - walk) < 1e-5
+    assert gi[2, 0] == 0 and gi[n - 3, 0] == 1                            # each end owns its side of the strip
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_faces,M,K", [(2_000, 40, 4), (20_000, 300, 4), (5_000, 64, 8)])
+def test_geodesic_mode_matches_dijkstra(n_faces, M, K):
+    from dreammesh4d_b200.deform_graph import build_deformation_graph, geodesic_knn_nodes, sample_surface_points
+    verts, faces = synthetic.uv_sphere(n_faces)
+    g = torch.Generator().manual_seed(M)
+    verts = verts * (1.0 + 0.3 * torch.sin(5 * verts[:, :1]))              # a bumpy, non-convex surface
+    nodes = sample_surface_points(verts, faces, M, seed=3)
+    idx, dist = geodesic_knn_nodes(verts.cuda(), faces.cuda(), nodes.cuda(), K + 1)
+    ridx, rdist = GO.geodesic_knn(verts.numpy(), faces.numpy(), nodes.numpy(), K + 1)
+    # path lengths agree to fp32 accumulation; the neighbour sets agree wherever the oracle's ranking is not a near-tie
+    assert np.abs(dist.cpu().numpy() - rdist).max() <= 2e-5 * max(rdist.max(), 1.0)
+    gap = np.diff(rdist, axis=1).min(axis=1) > 1e-5          # the lattice of a UV sphere produces many exact ties
+    assert gap.mean() > 0.5
+    np.testing.assert_array_equal(idx.cpu().numpy()[gap], ridx[gap])
+    graph, conn = build_deformation_graph(verts.cuda(), nodes.cuda(), K, mode="geodisc", faces=faces.cuda())
+    i64, w = GO.build_geodisc(verts.numpy(), faces.numpy(), nodes.numpy(), K)
+    np.testing.assert_array_equal(graph.nbr_idx.cpu().numpy()[gap], i64[gap])
+    assert np.abs(graph.nbr_w.cpu().numpy()[gap] - w[gap]).max() <= 1e-4
+    assert np.allclose(graph.nbr_w.sum(-1).cpu().numpy(), 1.0, atol=1e-5)
