@@ -18,6 +18,7 @@ from . import rasterizer as R
 from .postops import post_ops
 from .camera import get_cam_info_gaussian
 from .geometry import DynamicSuGaRGeometry
+from .nvtx import nvtx_range
 
 
 class DiffGaussianBatchRenderer:
@@ -65,20 +66,23 @@ class DiffGaussianBatchRenderer:
                 geo.get_xyz, geo.get_opacity, geo.get_scaling, geo.get_rotation, colors, vp, H, W,
                 colors2=geo.get_gs_normals, means2D=screenspace, capacity=self.capacity, state_out=states)
         else:
-            timed = geo.deform(batch["timestamp"], node_attrs=node_attrs)       # one set per view
+            with nvtx_range("dm4d.skin"):
+                timed = geo.deform(batch["timestamp"], node_attrs=node_attrs)       # one set per view
             vp = R.make_view_params(view, proj, campos, tanx, tany, bg6, 1.0,
                                     set_index=torch.arange(B, device=dev))
-            color6, radii, depth, alpha = R.rasterize_batch(
-                timed["means3D"], geo.get_opacity, geo.get_scaling, timed["rotations"], geo.get_points_rgb(), vp, H, W,
-                colors2=timed["normals"], means2D=screenspace, capacity=self.capacity, distinct_sets=True,
-                state_out=states)
+            with nvtx_range("dm4d.rasterize"):
+                color6, radii, depth, alpha = R.rasterize_batch(
+                    timed["means3D"], geo.get_opacity, geo.get_scaling, timed["rotations"], geo.get_points_rgb(), vp, H, W,
+                    colors2=timed["normals"], means2D=screenspace, capacity=self.capacity, distinct_sets=True,
+                    state_out=states)
         self.last_state = states[0]
         self.last_view_params = vp        # [B,48] camera block actually rasterized (include/dm4d.h layout)
         # image post-ops (temporal.py:180-193,212-218,229 / normal.py:172-206) for the whole batch: one fused
         # forward kernel, outputs already [B,H,W,C]; its backward feeds the rasterizer backward directly
         nfd = compute_normal_from_dist and "rays_o" in batch
-        out = post_ops(color6, depth, alpha, batch["rays_o"] if nfd else None, batch["rays_d"] if nfd else None,
-                       static=static, compute_normal_from_dist=nfd)
+        with nvtx_range("dm4d.postops"):
+            out = post_ops(color6, depth, alpha, batch["rays_o"] if nfd else None, batch["rays_d"] if nfd else None,
+                           static=static, compute_normal_from_dist=nfd)
         out.update({
             "viewspace_points": screenspace,                                    # [B,P,3]; .grad holds the 2-D mean gradients
             "visibility_filter": list((radii > 0).unbind(0)),

@@ -22,6 +22,8 @@ from typing import Any, Dict, Optional, Sequence, Union
 import torch
 import torch.nn.functional as F
 
+from .nvtx import nvtx_range
+
 
 def ddim_alphas_cumprod(num_train_timesteps: int, beta_start: float, beta_end: float) -> torch.Tensor:
     """``DDIMScheduler(..., beta_schedule="scaled_linear").alphas_cumprod`` as the reference builds it (:138-155):
@@ -138,15 +140,17 @@ class TemporalStableZero123SDS:
         if rgb_as_latents:
             latents = F.interpolate(rgb_bchw, (32, 32), mode="bilinear", align_corners=False) * 2 - 1
         else:
-            latents = self.encode_images(F.interpolate(rgb_bchw, (256, 256), mode="bilinear", align_corners=False),
-                                         generator)
+            with nvtx_range("dm4d.sds.encode"):
+                latents = self.encode_images(F.interpolate(rgb_bchw, (256, 256), mode="bilinear", align_corners=False),
+                                             generator)
         cond = self.get_cond(elevation, azimuth, camera_distances, frame_indices)
         t = torch.randint(self.min_step, self.max_step + 1, [B], dtype=torch.long, device=latents.device,
                           generator=generator)
         with torch.no_grad():
             noise = torch.empty_like(latents).normal_(generator=generator)      # == randn_like (follows latents' memory format)
             noisy = add_noise(self.alphas, latents, noise, t)
-            eps = self.model.apply_model(torch.cat([noisy, noisy]).to(self.weights_dtype), torch.cat([t, t]), cond)
+            with nvtx_range("dm4d.sds.unet"):
+                eps = self.model.apply_model(torch.cat([noisy, noisy]).to(self.weights_dtype), torch.cat([t, t]), cond)
             eps_uncond, eps_cond = eps.chunk(2)
             eps = eps_uncond + self.guidance_scale * (eps_cond - eps_uncond)
             w = (1.0 - self.alphas.to(latents.device)[t]).reshape(-1, 1, 1, 1)

@@ -24,6 +24,7 @@ import torch.distributed as dist
 from . import _lib
 from .camera import get_cam_info_gaussian
 from .geometry import DynamicSuGaRGeometry, activate_node_deltas
+from .nvtx import nvtx_range
 from .renderer import DiffGaussianBatchRenderer
 
 
@@ -152,13 +153,16 @@ class DynamicStageStep:
             live = geo.get_timed_dg_attributes(ts_all)             # autograd graph kept: no replay needed
         leaves = [None if t is None else t.detach().requires_grad_(True) for t in live]
         total, off = None, 0
-        for batch in batches:
+        for bi, batch in enumerate(batches):
             n = batch["timestamp"].shape[0]
             node = [None if t is None else t[off:off + n] for t in leaves]
-            out = self.ren.batch_forward(batch, node_attrs=node)
+            with nvtx_range(f"dm4d.substep{bi}.forward"):
+                out = self.ren.batch_forward(batch, node_attrs=node)
             self._note_overflow()
-            loss = self.loss_fn(out, batch)
-            loss.backward()                                    # ... down to the control-node attributes
+            with nvtx_range(f"dm4d.substep{bi}.loss"):
+                loss = self.loss_fn(out, batch)
+            with nvtx_range(f"dm4d.substep{bi}.backward"):
+                loss.backward()                                # ... down to the control-node attributes
             total = loss.detach() if total is None else total + loss.detach()
             off += n
             geo.update_step(0, step)                           # per-substep caches (dynamic_sugar.py:863-873)
@@ -169,8 +173,10 @@ class DynamicStageStep:
             pairs = [(a, g) for a, g in zip(live, grads) if a is not None and g is not None]
             torch.autograd.backward([a for a, _ in pairs], [g for _, g in pairs])
             if multi:
-                self.bucket.all_reduce(self.group)             # the step's one exchange
-        self.opt.step()
+                with nvtx_range("dm4d.exchange"):
+                    self.bucket.all_reduce(self.group)         # the step's one exchange
+        with nvtx_range("dm4d.optimizer"):
+            self.opt.step()
         self._calls += 1
         if self.overflow_check_every > 0 and self._calls % self.overflow_check_every == 0 and \
                 not torch.cuda.is_current_stream_capturing():
