@@ -42,6 +42,29 @@ def activate_node_deltas(trans, rot_delta, strain6, opacity_delta):
     return trans, rot, scale, opacity
 
 
+def deformed_gaussian_scales(node_scale: torch.Tensor, node_opacity: Optional[torch.Tensor], nbr_idx: torch.Tensor,
+                             nbr_w: torch.Tensor, faces: torch.Tensor, bary: torch.Tensor, scaling: torch.Tensor,
+                             method: str) -> torch.Tensor:
+    """``d_scale=True`` (the reference's class default, off in the shipped YAML): per-Gaussian scale vectors [T,P,3] =
+    (barycentric blend over the face's vertices of the blended node scale matrices) x static scaling vector.
+    Vertex matrices (dynamic_sugar.py:595-612): LBS ``sum_k w_k S_k``; hybrid ``sum_k w_k o_k S_k + (1 - lambda) I`` with
+    ``lambda = min(1, sum_k w_k o_k + 0.4)`` (:571-577); Gaussian scales (:698-704).  Plain tensor ops (autograd gives
+    the gradients to the node attributes): an optional branch, not part of the fused skinning kernels."""
+    if method == "dqs":
+        raise ValueError("d_scale is undefined for skinning_method='dqs' (the reference produces no vertex scale there)")
+    Sn = node_scale[:, nbr_idx]                                            # [T,V,K,3,3]
+    w = nbr_w[None, ..., None, None]
+    if method == "lbs":
+        Sv = (w * Sn).sum(dim=-3)
+    else:
+        on = node_opacity.reshape(node_opacity.shape[0], -1, 1)[:, nbr_idx]   # [T,V,K,1]
+        lam = ((nbr_w[None, ..., None] * on).sum(dim=-2) + 0.4).clamp(max=1.0)
+        Sv = (w * on[..., None] * Sn).sum(dim=-3) + (1.0 - lam)[..., None] * torch.eye(3, dtype=Sn.dtype, device=Sn.device)
+    T, F_, g = Sv.shape[0], faces.shape[0], bary.shape[0]
+    Sg = (bary[None, None, :, :, None, None] * Sv[:, faces][:, :, None]).sum(dim=-3)       # [T,F,g,3,3]
+    return (Sg.reshape(T, F_ * g, 3, 3) @ scaling[None, ..., None]).squeeze(-1)
+
+
 def exp_interp(value, step: int) -> float:
     """threestudio ``C(value, 0, step, interpolation="exp")`` (threestudio/utils/misc.py:66-101) for the learning-rate
     schedules of sugar.py:387-404 / dynamic_sugar.py:230-279: a number, or [start_step, v0, v1, end_step]."""
@@ -89,6 +112,7 @@ class SuGaRState:
                        learn: Optional[Dict[str, bool]] = None) -> None:
         self.g = scene.g
         self.skinning_method = skinning_method
+        self.d_scale = False                      # see deformed_gaussian_scales
         self.thickness = float(scene.thickness)
         lr = dict(points=static_learnable, scales=static_learnable, quaternions=static_learnable,
                   densities=static_learnable, sh=static_learnable)
@@ -195,6 +219,10 @@ class SuGaRState:
             method=self.skinning_method)
         self._timed = {"timestamp": timestamp, "key": (timestamp.data_ptr(), timestamp._version, tuple(timestamp.shape)),
                        "means3D": means, "rotations": rots, "normals": normals, "verts": verts, "vert_rot": vrot}
+        if self.d_scale:
+            self._timed["scales"] = deformed_gaussian_scales(
+                scale, opac, self._xyz_neighbor_node_idx, self._xyz_neighbor_nodes_weights, self._surface_mesh_faces,
+                self.surface_triangle_bary_coords[..., 0], self.get_scaling, self.skinning_method)
         return self._timed
 
     def _timed_for(self, timestamp: torch.Tensor) -> dict:
@@ -217,7 +245,8 @@ class SuGaRState:
     def get_timed_gs_all_single_time(self, timestamp=None, frame_idx=None):
         """dynamic_sugar.py:708-724 — (means3D, scales, rotations, opacity, colors_precomp) of one view."""
         t = self._timed_for(timestamp.reshape(1))
-        return t["means3D"][0], self.get_scaling, t["rotations"][0], self.get_opacity, self.get_points_rgb()
+        scales = t["scales"][0] if "scales" in t else self.get_scaling
+        return t["means3D"][0], scales, t["rotations"][0], self.get_opacity, self.get_points_rgb()
 
     def get_timed_gs_normals(self, timestamp=None, frame_idx=None):
         """dynamic_sugar.py:357-364 — [N_t, P, 3]."""

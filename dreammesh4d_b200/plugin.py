@@ -215,9 +215,9 @@ class DynamicSuGaRModel(SuGaRModel):
             # a different parametrisation (no control graph) that the hot path does not cover
             raise NotImplementedError("dreammesh4d_b200 covers dynamic_mode='deformation' with use_deform_graph=True "
                                       "(the configuration of configs/sugar_dynamic_dg.yaml)")
-        if c.d_scale:
-            raise NotImplementedError("d_scale=True (per-Gaussian scale deformation, dynamic_sugar.py:595-612,698-704) is not "
-                                      "built; configs/sugar_dynamic_dg.yaml sets d_scale: false")
+        if c.d_scale and c.skinning_method == "dqs":
+            raise ValueError("d_scale=True with skinning_method='dqs': the reference produces no vertex scale there "
+                             "(dynamic_sugar.py:595-612) and fails with a KeyError at :699")
         _TSGeometry.configure(self)
         self.active_sh_degree, self.sh_levels = 0, c.sh_levels
         scene = self._bind_mesh(o3d_mesh)
@@ -228,6 +228,7 @@ class DynamicSuGaRModel(SuGaRModel):
         self._install_state(scene, None, net, skinning_method=c.skinning_method, static_learnable=c.static_learnable,
                             sh_levels=c.sh_levels, learn=learn)
         self.to(self.device)
+        self.d_scale = bool(c.d_scale)            # per-Gaussian scale deformation: tensor ops on top of the fused kernels
         self.num_frames, self.dynamic_mode = c.num_frames, c.dynamic_mode
         self.build_deformation_graph(c.n_dg_nodes, xyz_nodes, nodes_connectivity=c.dg_node_connectivity, mode=c.dist_mode)
         self.spatial_lr_scale = c.spatial_lr_scale

@@ -72,7 +72,7 @@ class DiffGaussianBatchRenderer:
                                     set_index=torch.arange(B, device=dev))
             with nvtx_range("dm4d.rasterize"):
                 color6, radii, depth, alpha = R.rasterize_batch(
-                    timed["means3D"], geo.get_opacity, geo.get_scaling, timed["rotations"], geo.get_points_rgb(), vp, H, W,
+                    timed["means3D"], geo.get_opacity, timed.get("scales", geo.get_scaling), timed["rotations"], geo.get_points_rgb(), vp, H, W,
                     colors2=timed["normals"], means2D=screenspace, capacity=self.capacity, distinct_sets=True,
                     state_out=states)
         self.last_state = states[0]

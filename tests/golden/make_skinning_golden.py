@@ -200,8 +200,10 @@ def main():
                 setattr(Ref, k.split(".")[1], list(loc.values())[0])
 
     from dreammesh4d_b200 import synthetic
-    for tag, dtype, g, method in (("f64_g3_hybrid", torch.float64, 3, "hybrid"), ("f32_g6_hybrid", torch.float32, 6, "hybrid"),
-                                  ("f64_g3_lbs", torch.float64, 3, "lbs"), ("f64_g3_dqs", torch.float64, 3, "dqs")):
+    for tag, dtype, g, method, d_scale in (("f64_g3_hybrid", torch.float64, 3, "hybrid", False), ("f32_g6_hybrid", torch.float32, 6, "hybrid", False),
+                                           ("f64_g3_lbs", torch.float64, 3, "lbs", False), ("f64_g3_dqs", torch.float64, 3, "dqs", False),
+                                           ("f64_g3_hybrid_dscale", torch.float64, 3, "hybrid", True),
+                                           ("f64_g3_lbs_dscale", torch.float64, 3, "lbs", True)):
         torch.manual_seed(0)
         scene = synthetic.make_sugar_scene(264, g=g)        # 12 x 11 UV sphere
         gen = torch.Generator().manual_seed(3)
@@ -216,7 +218,7 @@ def main():
         c = lambda t: t.to(dtype)
 
         r = Ref()
-        r.cfg = types.SimpleNamespace(skinning_method=method, d_scale=False, use_deform_graph=True,
+        r.cfg = types.SimpleNamespace(skinning_method=method, d_scale=d_scale, use_deform_graph=True,
                                       n_gaussians_per_surface_triangle=g, sh_levels=1)
         r.device = "cpu"
         r.binded_to_surface_mesh = True
@@ -264,6 +266,7 @@ def main():
             out_static_normals=r.get_gs_normals.numpy(),
             out_single_means=m1.numpy(), out_single_scales=s1.numpy(), out_single_rot=r1.numpy(),
             out_single_opacity=o1.numpy(), out_single_colors=c1.numpy(),
+            **({"out_vert_scale": vert["scale"].numpy(), "out_gs_scale": gs["scale"].numpy()} if d_scale else {}),
         )
         print("wrote", f"skinning_{tag}.npz", "V", r._points.shape[0], "P", scene.n_gaussians)
 

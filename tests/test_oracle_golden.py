@@ -85,3 +85,19 @@ def test_identity_deformation_is_identity():
         assert (out["means3D"] - static[None]).abs().max() < 1e-6
         s = torch.sign((out["rotations"] * out["rest_quat"][None]).sum(-1, keepdim=True))
         assert (out["rotations"] * s - out["rest_quat"][None]).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["f64_g3_hybrid_dscale", "f64_g3_lbs_dscale"])
+def test_d_scale_branch_reproduces_reference(tag):
+    """``d_scale=True`` (dynamic_sugar.py:595-612, 698-704): per-Gaussian scales against the outputs of the reference's own
+    code (tests/golden/make_skinning_golden.py).  The product function is plain tensor ops, so it is checked here on the CPU."""
+    from dreammesh4d_b200.geometry import deformed_gaussian_scales
+    z = np.load(GOLD / f"skinning_{tag}.npz")
+    t = lambda k: torch.from_numpy(z[k])
+    scaling = torch.from_numpy(z["out_static_scaling"])
+    got = deformed_gaussian_scales(t("node_scale"), t("node_opacity"), t("nbr_idx"), t("nbr_w"), t("faces"), t("bary"), scaling,
+                                   str(z["method"]))
+    assert float((got - t("out_gs_scale")).abs().max()) <= 1e-12
+    assert float((got[1] - t("out_single_scales")).abs().max()) <= 1e-12
+    with pytest.raises(ValueError):
+        deformed_gaussian_scales(t("node_scale"), None, t("nbr_idx"), t("nbr_w"), t("faces"), t("bary"), scaling, "dqs")

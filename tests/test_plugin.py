@@ -139,3 +139,24 @@ def test_static_stage_objects_build_from_cfg():
     (out["comp_rgb"].mean() + out["comp_normal"].mean()).backward()
     assert geo._points.grad is not None and float(geo._points.grad.abs().max()) > 0
     assert geo.surface_mesh.verts_list()[0].shape == (V, 3)
+
+
+@pytest.mark.gpu
+def test_d_scale_true_flows_through_the_batched_renderer():
+    """Class default ``d_scale=True`` (dynamic_sugar.py:68): per-timestamp Gaussian scales reach the rasterizer as one
+    attribute set per view and their gradient reaches the scale head of the deformation network."""
+    mesh, V, F = _mesh()
+    geo = plugin.REGISTRY["dynamic-sugar"](dict(n_dg_nodes=32, dg_node_connectivity=4, d_scale=True, skinning_method="hybrid",
+                                               spatial_extent=1.0, n_gaussians_per_surface_triangle=3, init_gs_opacity=0.9,
+                                               surface_mesh_to_bind_path="x.obj"), mesh)
+    ren = plugin.REGISTRY["diff-sugar-rasterizer-temporal"]({}, geometry=geo, material=None, background=None)
+    with torch.no_grad():
+        geo._deformation.deformation_net.scales_deform.feature_out[1].weight.normal_(0, 0.05)
+    c2w, fovy = synthetic.random_orbit_cameras(2, seed=5)
+    batch = {"c2w": c2w.cuda(), "fovy": fovy.cuda(), "height": 64, "width": 64, "timestamp": torch.tensor([0.3, 0.6], device="cuda")}
+    out = ren.batch_forward(batch)
+    assert geo._timed["scales"].shape == (2, 3 * F, 3)
+    assert not torch.allclose(geo._timed["scales"][0], geo.get_scaling)
+    out["comp_rgb"].square().mean().backward()
+    g = geo._deformation.deformation_net.scales_deform.feature_out[1].weight.grad
+    assert g is not None and float(g.abs().max()) > 0
