@@ -46,7 +46,7 @@ class SkinDesc(ctypes.Structure):
         ("g", c_int32), ("method", c_int32), ("reserved0", c_int32),
         ("rest_verts", c_void_p), ("faces", c_void_p), ("nbr_idx", c_void_p), ("nbr_w", c_void_p),
         ("bary", c_void_p), ("rest_quat", c_void_p), ("node_trans", c_void_p), ("node_rot", c_void_p),
-        ("node_scale", c_void_p), ("node_opacity", c_void_p),
+        ("node_scale", c_void_p), ("node_opacity", c_void_p), ("node_inc_ptr", c_void_p), ("node_inc", c_void_p), ("vert_scratch", c_void_p),
     ]
 
 
@@ -78,6 +78,7 @@ SIGNATURES = {
     "dm4d_raster_export_state": (ctypes.c_int, [POINTER(RasterDesc), c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "dm4d_skin_forward": (ctypes.c_int, [POINTER(SkinDesc)] + [c_void_p] * 6),
     "dm4d_skin_backward": (ctypes.c_int, [POINTER(SkinDesc)] + [c_void_p] * 14),
+    "dm4d_skin_node_incidence": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dm4d_sugar_rest_frames": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dm4d_sugar_rest_frames_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dm4d_arap_energy": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -19,10 +19,11 @@ LIB = LIBDIR / "libdm4d.so"
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-# translation unit -> extra flags.  raster_preprocess.cu and skin.cu carry the bit-exact arithmetic
+# translation unit -> extra flags.  raster_preprocess.cu carries the bit-exact arithmetic
 # spec (no FMA contraction); the render kernels are compiled with default contraction.
 UNITS = {
     "raster_preprocess.cu": ["-fmad=false"],
+    "raster_preprocess_bwd.cu": [],
     "raster_binning.cu": [],
     "raster_render.cu": [],
     "skin.cu": [],
@@ -45,12 +46,25 @@ def sources() -> list[Path]:
     return [CSRC / u for u in UNITS if (CSRC / u).exists()]
 
 
+def source_hash() -> str:
+    """Content hash of everything the library is built from (sources, headers, flags)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "dm4d.h"]
+    for p in deps:
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(repr((ARCH, COMMON, sorted(UNITS.items()), os.environ.get("DM4D_NVCC_EXTRA", ""))).encode())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not LIB.exists():
+    """Stale = the .so was not built from the sources as they are now (content hash, not mtime: the library travels
+    between machines with the repo snapshot)."""
+    stamp = LIB.with_suffix(".so.srchash")
+    if not LIB.exists() or not stamp.exists():
         return True
-    t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "dm4d.h"]
-    return any(p.stat().st_mtime > t for p in deps)
+    return stamp.read_text().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False, out: Path | None = None, extra: str | None = None) -> Path:
@@ -88,6 +102,8 @@ def build(force: bool = False, verbose: bool = False, out: Path | None = None, e
     if r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    if out is None:
+        LIB.with_suffix(".so.srchash").write_text(source_hash() + "\n")
     return target
 
 

@@ -16,7 +16,7 @@ void dm4d_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* dm4d_last_error(void) { return g_err; }
-extern "C" int dm4d_version(void) { return 130; }   // 1.3: segmented front-to-back backward (takes the forward's colour / depth images), groupnorm_nhwc
+extern "C" int dm4d_version(void) { return 140; }   // 1.4: node-centric skinning backward (dm4d_skin_node_incidence, two desc fields)
 
 void raster_sizes(int P, int H, int W, int n_views, int channels, long long capacity, uint64_t* geom, uint64_t* bin,
                   uint64_t* img, uint64_t* bwd) {

@@ -13,6 +13,7 @@
 //      with TMA bulk copies.
 // Order = ascending (tile, depth bits, Gaussian id) — exactly the order of upstream's stable radix
 // sort fed in ascending-id emission order, independent of atomics ordering.
+#include <algorithm>
 #include "raster_internal.cuh"
 
 namespace {
@@ -167,14 +168,6 @@ __global__ void __launch_bounds__(DM4D_BLOCK) scatter_kernel(RasterLayout L) {
 }
 
 // ---- per-tile sort ------------------------------------------------------------------------------
-#ifndef DM4D_SORT_CHUNK
-#define DM4D_SORT_CHUNK 4096
-#endif
-#ifndef DM4D_SORT_THREADS
-#define DM4D_SORT_THREADS 512
-#endif
-constexpr int SORT_CHUNK = DM4D_SORT_CHUNK;     // keys held in shared memory (8 B each)
-constexpr int SORT_THREADS = DM4D_SORT_THREADS;
 constexpr unsigned long long KEY_INF = 0xffffffffffffffffull;
 
 // Single-direction bitonic network on `n` real keys padded virtually with +inf up to `npow2`:
@@ -242,8 +235,8 @@ __device__ void smem_network(unsigned long long* sk, int cn /* pow2 <= SORT_CHUN
     }
 }
 
-// Block-level merge sort of `n` keys held in shared memory (n <= SORT_CHUNK): every thread first sorts MS_E
-// consecutive keys in registers, then log2(n / MS_E) merge passes in which each thread produces MS_E consecutive
+// Block-level merge sort of `n` keys held in shared memory (n <= E * blockDim.x): every thread first sorts E
+// consecutive keys in registers, then log2(n / E) merge passes in which each thread produces E consecutive
 // outputs of its pair of runs (merge-path binary search for the split, then a sequential merge).  About 4x
 // fewer instructions per key than the bitonic network; keys are unique, so the result is the unique sorted order.
 constexpr int MS_E = 8;
@@ -253,26 +246,50 @@ __device__ __forceinline__ void cmpswap(unsigned long long& a, unsigned long lon
     a = lo; b = hi;
 }
 
-__device__ void smem_merge_sort(unsigned long long* sk, int n) {
-    const int npad = (n + MS_E - 1) / MS_E * MS_E;
-    const int base = threadIdx.x * MS_E;
-    const bool active = base < npad;
-    unsigned long long r[MS_E];
-    if (active) {
-#pragma unroll
-        for (int e = 0; e < MS_E; ++e) r[e] = sk[base + e];
-        // odd-even merge sorting network for 8 keys (19 comparators)
+// Sorting network on E (power of two) keys in registers; every index is a compile-time constant after unrolling.
+// E = 8: Batcher's odd-even merge sort (19 comparators); larger E: bitonic (simple loop nest that always unrolls).
+template <int E>
+__device__ __forceinline__ void sort_registers(unsigned long long (&r)[E]) {
+    if constexpr (E == 8) {
         cmpswap(r[0], r[1]); cmpswap(r[2], r[3]); cmpswap(r[4], r[5]); cmpswap(r[6], r[7]);
         cmpswap(r[0], r[2]); cmpswap(r[1], r[3]); cmpswap(r[4], r[6]); cmpswap(r[5], r[7]);
         cmpswap(r[1], r[2]); cmpswap(r[5], r[6]);
         cmpswap(r[0], r[4]); cmpswap(r[1], r[5]); cmpswap(r[2], r[6]); cmpswap(r[3], r[7]);
         cmpswap(r[2], r[4]); cmpswap(r[3], r[5]);
         cmpswap(r[1], r[2]); cmpswap(r[3], r[4]); cmpswap(r[5], r[6]);
+    } else {
 #pragma unroll
-        for (int e = 0; e < MS_E; ++e) sk[base + e] = r[e];
+        for (int k = 2; k <= E; k <<= 1) {
+#pragma unroll
+            for (int i = 0; i < E; ++i) {                       // flip step: i <-> its mirror inside the k-block
+                const int l = (i & ~(k - 1)) + (k - 1 - (i & (k - 1)));
+                if (l > i) cmpswap(r[i], r[l]);
+            }
+#pragma unroll
+            for (int j = k >> 2; j > 0; j >>= 1) {
+#pragma unroll
+                for (int i = 0; i < E; ++i)
+                    if ((i & j) == 0) cmpswap(r[i], r[i | j]);
+            }
+        }
+    }
+}
+
+template <int E>
+__device__ void smem_merge_sort(unsigned long long* sk, int n) {
+    const int npad = (n + E - 1) / E * E;
+    const int base = threadIdx.x * E;
+    const bool active = base < npad;
+    unsigned long long r[E];
+    if (active) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) r[e] = sk[base + e];
+        sort_registers<E>(r);
+#pragma unroll
+        for (int e = 0; e < E; ++e) sk[base + e] = r[e];
     }
     __syncthreads();
-    for (int w = MS_E; w < npad; w <<= 1) {
+    for (int w = E; w < npad; w <<= 1) {
         if (active) {
             const int a0 = base & ~(2 * w - 1);            // start of this thread's pair of runs
             const int b0 = a0 + w;
@@ -280,7 +297,7 @@ __device__ void smem_merge_sort(unsigned long long* sk, int n) {
             const int lenB = max(0, min(w, npad - b0));
             const unsigned long long* A = sk + a0;
             const unsigned long long* B = sk + b0;
-            const int diag = base - a0;                      // outputs [diag, diag + MS_E) of the merged pair
+            const int diag = base - a0;                      // outputs [diag, diag + E) of the merged pair
             int lo = max(0, diag - lenB), hi = min(diag, lenA);
             while (lo < hi) {                                // merge path: number of A elements among the first `diag`
                 const int mid = (lo + hi) >> 1;
@@ -289,7 +306,7 @@ __device__ void smem_merge_sort(unsigned long long* sk, int n) {
             int i = lo, j = diag - lo;
             unsigned long long av = i < lenA ? A[i] : KEY_INF, bv = j < lenB ? B[j] : KEY_INF;
 #pragma unroll
-            for (int e = 0; e < MS_E; ++e) {
+            for (int e = 0; e < E; ++e) {
                 const bool takeA = (j >= lenB) || (i < lenA && av <= bv);
                 r[e] = takeA ? av : bv;
                 if (takeA) { ++i; av = i < lenA ? A[i] : KEY_INF; }
@@ -299,7 +316,7 @@ __device__ void smem_merge_sort(unsigned long long* sk, int n) {
         __syncthreads();
         if (active) {
 #pragma unroll
-            for (int e = 0; e < MS_E; ++e) sk[base + e] = r[e];
+            for (int e = 0; e < E; ++e) sk[base + e] = r[e];
         }
         __syncthreads();
     }
@@ -389,43 +406,47 @@ __device__ __forceinline__ void pack_tile(const unsigned long long* keys, int n,
     }
 }
 
-// Two CTA sizes share the tiles by segment length: 128 threads up to 1024 keys, 512 above (at C3 a tile holds ~1100
-// instances: a 512-thread CTA runs its merge passes with a quarter of its threads while the others wait at the pass
-// barriers; small CTAs keep more tiles resident per SM and their barriers span 4 warps).  Measured at C3: one size
-// 0.365 ms, two sizes 0.319 ms, three sizes (128/256/512) 0.372 ms — every extra launch adds its own tail.
-template <int THREADS, int CHUNK, int R4>
-__global__ void __launch_bounds__(THREADS) sort_pack_kernel(RasterLayout L, int n_lo, int n_hi) {
-    constexpr int SORT_CHUNK = CHUNK;
-    constexpr int SORT_THREADS = THREADS;
-    extern __shared__ __align__(16) unsigned long long sk[];   // [CHUNK]
+// Three CTA shapes share the tiles by segment length, all sorting in shared memory: 128 threads x 8 keys up to 1024
+// keys, 512 x 8 up to 4096, 1024 x 16 up to 16384 (128 KB of shared memory; the limb / centre tiles of C3 hold ~6000
+// instances, C4's densest ~10^4).  Small CTAs keep more tiles resident per SM and their pass barriers span 4 warps.
+// Only segments above 16384 keys fall back to chunked bitonic merging through global memory — that path took 0.25 ms for
+// a 6000-key tile and was the whole tail of the launch when the largest in-memory tier was 4096.
+template <int THREADS, int E, int R4>
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : (THREADS == 512 ? 3 : 10)) sort_pack_kernel(RasterLayout L, int n_lo, int n_hi) {
+    constexpr int SORT_CHUNK = THREADS * E;
+    extern __shared__ __align__(16) unsigned long long sk[];   // [SORT_CHUNK]
     if (L.hdr->overflow) return;
-    const int tile = (int)L.tile_order[blockIdx.x];   // global (view, tile) index, heaviest first
+    // tile_order is sorted by floor(log2(count)) descending: a CTA walks the list grid-stride and stops at the first
+    // tile below its tier's range (the heavy tiers run as a few persistent CTAs over the head of the list)
+    const int n_all = L.n_views * L.tiles;
+    for (int it = blockIdx.x; it < n_all; it += gridDim.x) {
+    const int tile = (int)L.tile_order[it];           // global (view, tile) index, heaviest first
     const unsigned int beg = L.tile_offset[tile];
     const int n = (int)(L.tile_offset[tile + 1] - beg);
-    if (n <= n_lo || n > n_hi) return;
+    if (__clz(n) > __clz(n_lo + 1)) break;
+    if (n <= n_lo || n > n_hi) continue;
+    __syncthreads();                                  // the previous tile's pack still reads sk
     const int v = tile / L.tiles;
     unsigned long long* gk = L.keys + beg;
-    int npow2 = 2;
-    while (npow2 < n) npow2 <<= 1;
-
     const float4* grec = reinterpret_cast<const float4*>(L.g_rec + (size_t)v * L.P * L.rec);
     float4* srec = reinterpret_cast<float4*>(L.stream + (size_t)beg * L.rec);
     const float tile_y0 = (float)(((tile - v * L.tiles) / L.gx) * DM4D_TILE);
     const float tile_x0 = (float)(((tile - v * L.tiles) % L.gx) * DM4D_TILE);
 
-    if (npow2 <= SORT_CHUNK) {
-        const int nfill = max(npow2, (n + MS_E - 1) / MS_E * MS_E);      // the merge sort pads to a multiple of MS_E
+    if (n <= SORT_CHUNK) {
+        const int nfill = (n + E - 1) / E * E;                       // the merge sort pads to a multiple of E
         for (int i = threadIdx.x; i < nfill; i += blockDim.x) sk[i] = i < n ? gk[i] : KEY_INF;
         __syncthreads();
-        if (MS_E * SORT_THREADS >= SORT_CHUNK) smem_merge_sort(sk, n);
-        else smem_network(sk, npow2, 2, npow2);
+        smem_merge_sort<E>(sk, n);
         __syncthreads();
         pack_tile<R4>(sk, n, grec, srec, tile_x0, tile_y0);
-        return;
+        continue;
     }
 
-    // Large segment: sort SORT_CHUNK-sized chunks in shared memory, then merge with global
+    // Very large segment: sort SORT_CHUNK-sized chunks in shared memory, then merge with global
     // compare-exchange steps for strides >= SORT_CHUNK and shared-memory steps below.
+    int npow2 = 2;
+    while (npow2 < n) npow2 <<= 1;
     const int nchunks = npow2 / SORT_CHUNK;
     for (int c = 0; c < nchunks; ++c) {
         const int base = c * SORT_CHUNK;
@@ -466,6 +487,7 @@ __global__ void __launch_bounds__(THREADS) sort_pack_kernel(RasterLayout L, int 
     }
     __syncthreads();
     pack_tile<R4>(gk, n, grec, srec, tile_x0, tile_y0);
+    }
 }
 
 __global__ void export_state_kernel(RasterLayout L, int view, unsigned int* ranges, unsigned int* point_list,
@@ -486,21 +508,40 @@ __global__ void export_state_kernel(RasterLayout L, int view, unsigned int* rang
 
 }  // namespace
 
-#ifndef DM4D_SORT_SMALL_THREADS
-#define DM4D_SORT_SMALL_THREADS 128      // CTA size of the small-segment instantiation (8 keys per thread)
-#endif
 template <int R4>
 int launch_sort_pack_t(const RasterLayout& L, cudaStream_t s) {
     static bool configured = false;
-    const size_t smem = (size_t)SORT_CHUNK * sizeof(unsigned long long);
+    constexpr int K_S = 128 * 8, K_M = 512 * 8, K_L = 1024 * 8, K_X = 1024 * 16;
     if (!configured) {
-        DM4D_CUDA_CHECK(cudaFuncSetAttribute(sort_pack_kernel<SORT_THREADS, SORT_CHUNK, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DM4D_CUDA_CHECK(cudaFuncSetAttribute(sort_pack_kernel<512, 8, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, K_M * 8));
+        DM4D_CUDA_CHECK(cudaFuncSetAttribute(sort_pack_kernel<1024, 8, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, K_L * 8));
+        DM4D_CUDA_CHECK(cudaFuncSetAttribute(sort_pack_kernel<1024, 16, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, K_X * 8));
         configured = true;
     }
-    const unsigned grid = (unsigned)(L.n_views * L.tiles);
-    constexpr int SMALL_KEYS = MS_E * DM4D_SORT_SMALL_THREADS;
-    sort_pack_kernel<SORT_THREADS, SORT_CHUNK, R4><<<grid, SORT_THREADS, smem, s>>>(L, SMALL_KEYS, 0x7fffffff);
-    sort_pack_kernel<DM4D_SORT_SMALL_THREADS, SMALL_KEYS, R4><<<grid, DM4D_SORT_SMALL_THREADS, SMALL_KEYS * sizeof(unsigned long long), s>>>(L, 0, SMALL_KEYS);
+    const int n_all = L.n_views * L.tiles;
+    auto grid = [&](int per_sm) { return (unsigned)std::max(1, std::min(n_all, 148 * per_sm)); };
+    // The four tiers are independent: fork them onto side streams (works inside a stream capture too — the side
+    // streams join the capture through the events), so the few CTAs of the heavy tiers (one 10^4-key tile takes a
+    // 1024-thread CTA ~0.1 ms) run under the bulk of the small tiles instead of in front of them.
+    static cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    static cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+    if (!fork_ev) {
+        for (int i = 0; i < 3; ++i) {
+            DM4D_CUDA_CHECK(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+            DM4D_CUDA_CHECK(cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming));
+        }
+        DM4D_CUDA_CHECK(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+    }
+    DM4D_CUDA_CHECK(cudaEventRecord(fork_ev, s));
+    for (int i = 0; i < 3; ++i) DM4D_CUDA_CHECK(cudaStreamWaitEvent(side[i], fork_ev, 0));
+    sort_pack_kernel<1024, 16, R4><<<grid(1), 1024, K_X * 8, side[0]>>>(L, K_L, 0x7fffffff);
+    sort_pack_kernel<1024, 8, R4><<<grid(1), 1024, K_L * 8, side[1]>>>(L, K_M, K_L);
+    sort_pack_kernel<512, 8, R4><<<grid(4), 512, K_M * 8, side[2]>>>(L, K_S, K_M);
+    sort_pack_kernel<128, 8, R4><<<(unsigned)n_all, 128, K_S * 8, s>>>(L, 0, K_S);
+    for (int i = 0; i < 3; ++i) {
+        DM4D_CUDA_CHECK(cudaEventRecord(join_ev[i], side[i]));
+        DM4D_CUDA_CHECK(cudaStreamWaitEvent(s, join_ev[i], 0));
+    }
     return DM4D_OK;
 }
 

@@ -65,25 +65,32 @@ __device__ __forceinline__ f3 so3_log(float4 q) {
     else f = 2.f / q.w - (2.f / 3.f) * n * n / (q.w * q.w * q.w);
     return f * v;
 }
-// dL/dq given g = dL/d(log q)
-__device__ __forceinline__ float4 so3_log_bwd(float4 q, f3 g) {
+// dL/dq given g = dL/d(log q):  f g + (g.v) c1 v  for the vector part, (g.v) c2 for w.  The three coefficients depend
+// on q only (hoisted out of the incidence loop of the node-centric backward).
+struct LogBwdCoef { float f, c1, c2; };
+__device__ __forceinline__ LogBwdCoef so3_log_bwd_coef(float4 q) {
     const f3 v = vec(q);
     const float n2 = dot(v, v), n = sqrtf(n2), w = q.w;
-    float f, dfdn_over_n, dfdw;
+    LogBwdCoef c;
     if (n > EPS_LIE) {
-        f = 2.f * atanf(n / w) / n;
+        c.f = 2.f * atanf(n / w) / n;
         const float s = w * w + n2;
-        dfdn_over_n = (2.f * w / s - f) / n2;
-        dfdw = -2.f / s;
+        c.c1 = (2.f * w / s - c.f) / n2;
+        c.c2 = -2.f / s;
     } else {
         const float w2 = w * w;
-        f = 2.f / w - (2.f / 3.f) * n2 / (w2 * w);
-        dfdn_over_n = -(4.f / 3.f) / (w2 * w);
-        dfdw = -2.f / w2 + 2.f * n2 / (w2 * w2);
+        c.f = 2.f / w - (2.f / 3.f) * n2 / (w2 * w);
+        c.c1 = -(4.f / 3.f) / (w2 * w);
+        c.c2 = -2.f / w2 + 2.f * n2 / (w2 * w2);
     }
-    const float gv = dot(g, v);
-    return mkq(f * g + (gv * dfdn_over_n) * v, gv * dfdw);
+    return c;
 }
+__device__ __forceinline__ float4 so3_log_bwd_apply(LogBwdCoef c, float4 q, f3 g) {
+    const f3 v = vec(q);
+    const float gv = dot(g, v);
+    return mkq(c.f * g + (gv * c.c1) * v, gv * c.c2);
+}
+__device__ __forceinline__ float4 so3_log_bwd(float4 q, f3 g) { return so3_log_bwd_apply(so3_log_bwd_coef(q), q, g); }
 __device__ __forceinline__ float4 so3_exp(f3 x) {
     const float th2 = dot(x, x), th = sqrtf(th2);
     float a, w;
@@ -110,6 +117,9 @@ __device__ __forceinline__ f3 so3_exp_bwd(f3 x, float4 g) {
 }
 
 __device__ __forceinline__ float4 ldq(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 struct SkinK {
     dm4d_skin_desc d;
@@ -179,97 +189,207 @@ struct SkinBwdK {
     int P;
     const float* verts; const float* vert_rot;
     const float* g_means; const float* g_rots; const float* g_normals;
-    float* dverts; float* dvert_rot;
+    float* dverts; float* dvert_rot;                       // scratch [n_t,V,4] each: gradients arriving from the faces
+    const float* dverts_in; const float* dvert_rot_in;     // optional direct gradients [n_t,V,3] / [n_t,V,4]
     float* dn_trans; float* dn_rot; float* dn_scale; float* dn_opac;
 };
 
-// Backward of one (timestamp, vertex): adds its contributions to the four node-gradient tables of timestamp t
-// (tT [M,3], tQ [M,4], tS [M,9], tO [M]) — global memory, or a per-CTA copy in shared memory.
-__device__ __forceinline__ void vertex_backward(const SkinBwdK& a, int t, int v, float* tT, float* tQ, float* tS, float* tO) {
+// Upstream gradients of one (timestamp, vertex): everything of its backward that does not depend on which of the K
+// neighbours is being differentiated.
+struct VertUp {
+    f3 x, dxi, dx_l; float dlam_raw; float4 dsq_r, dsq_d;
+};
+
+__device__ __forceinline__ void vertex_upstream(const SkinBwdK& a, int t, int v, VertUp& u) {
     const dm4d_skin_desc& d = a.d;
     const long long idx = (long long)t * d.V + v;
     const f3 x = ld3(d.rest_verts + (size_t)v * 3);
-    const f3 gx = ld3(a.dverts + (size_t)idx * 3);
-    const float4 gr = ldq(a.dvert_rot + (size_t)idx * 4);
+    f3 gx = vec(ldq(a.dverts + (size_t)idx * 4));
+    float4 gr = ldq(a.dvert_rot + (size_t)idx * 4);
+    if (a.dverts_in) gx = gx + ld3(a.dverts_in + (size_t)idx * 3);
+    if (a.dvert_rot_in) gr = gr + ldq(a.dvert_rot_in + (size_t)idx * 4);
     VertSums s;
     vertex_accumulate(d, t, v, x, s);
-
-    // rotation: r = exp(xi)
-    const f3 dxi = so3_exp_bwd(s.xi, gr);
-
-    // position
-    f3 dx_l = mk3(0, 0, 0);
-    float dlam_raw = 0.f;
-    float4 dsq_r = make_float4(0, 0, 0, 0), dsq_d = make_float4(0, 0, 0, 0);
-    if (d.method == 0) dx_l = gx;
+    u.x = x;
+    u.dxi = so3_exp_bwd(s.xi, gr);                       // rotation: r = exp(xi)
+    u.dx_l = mk3(0, 0, 0);
+    u.dlam_raw = 0.f;
+    u.dsq_r = make_float4(0, 0, 0, 0); u.dsq_d = make_float4(0, 0, 0, 0);
+    if (d.method == 0) { u.dx_l = gx; return; }
+    const float N2 = dot4(s.sq_r, s.sq_r), N = sqrtf(N2), inv = 1.f / N;
+    const float4 qn = inv * s.sq_r, dn = inv * s.sq_d;
+    f3 dx_d;
+    if (d.method == 1) dx_d = gx;
     else {
-        const float N2 = dot4(s.sq_r, s.sq_r), N = sqrtf(N2), inv = 1.f / N;
-        const float4 qn = inv * s.sq_r, dn = inv * s.sq_d;
-        f3 dx_d;
-        if (d.method == 1) dx_d = gx;
-        else {
-            const float lam_in = s.lam_raw + 0.4f;
-            const float lam = fminf(lam_in, 1.0f);
-            const f3 trans = vec(qmul(2.f * dn, qconj(qn)));
-            const f3 x_d = qact(qn, x) + trans;
-            dx_l = lam * gx;
-            dx_d = (1.f - lam) * gx;
-            if (lam_in <= 1.0f) dlam_raw = dot(gx, s.x_l - x_d);
-        }
-        // x_d = act(qn, x) + xyz(2 dn (x) conj(qn))
-        float4 dqn;
-        qact_bwd(qn, x, dx_d, dqn);
-        const float4 gm = mkq(dx_d, 0.f);                       // gradient of m = (2 dn) (x) conj(qn)
-        const float4 ddn = 2.f * qmul(gm, qn);                  // d/d(a) <g, a (x) b> = g (x) conj(b), b = conj(qn)
-        const float4 dconj = qmul(qconj(2.f * dn), gm);         // d/d(b) = conj(a) (x) g
-        dqn = dqn + make_float4(-dconj.x, -dconj.y, -dconj.z, dconj.w);
-        // qn = sq_r / N, dn = sq_d / N
-        const float c = (dot4(qn, dqn) + dot4(dn, ddn)) * inv;
-        dsq_r = inv * dqn + (-c) * qn;
-        dsq_d = inv * ddn;
+        const float lam_in = s.lam_raw + 0.4f;
+        const float lam = fminf(lam_in, 1.0f);
+        const f3 trans = vec(qmul(2.f * dn, qconj(qn)));
+        const f3 x_d = qact(qn, x) + trans;
+        u.dx_l = lam * gx;
+        dx_d = (1.f - lam) * gx;
+        if (lam_in <= 1.0f) u.dlam_raw = dot(gx, s.x_l - x_d);
     }
+    // x_d = act(qn, x) + xyz(2 dn (x) conj(qn))
+    float4 dqn;
+    qact_bwd(qn, x, dx_d, dqn);
+    const float4 gm = mkq(dx_d, 0.f);                       // gradient of m = (2 dn) (x) conj(qn)
+    const float4 ddn = 2.f * qmul(gm, qn);                  // d/d(a) <g, a (x) b> = g (x) conj(b), b = conj(qn)
+    const float4 dconj = qmul(qconj(2.f * dn), gm);         // d/d(b) = conj(a) (x) g
+    dqn = dqn + make_float4(-dconj.x, -dconj.y, -dconj.z, dconj.w);
+    // qn = sq_r / N, dn = sq_d / N
+    const float c = (dot4(qn, dqn) + dot4(dn, ddn)) * inv;
+    u.dsq_r = inv * dqn + (-c) * qn;
+    u.dsq_d = inv * ddn;
+}
 
+// Gradient of one (vertex, neighbour) incidence w.r.t. the node's attributes: g[0..2] translation, g[3..6] rotation
+// (xyzw), g[7..15] scale (row-major 3x3), g[16] opacity (lbs weight).  tr / q / S are the node's attributes at t.
+__device__ __forceinline__ void incidence_gradient(int method, float w, const VertUp& u, f3 tr, float4 q, LogBwdCoef lc,
+                                                   const float* S, float (&g)[17]) {
+    f3 dtr = mk3(0, 0, 0);
+    float4 dq = so3_log_bwd_apply(lc, q, w * u.dxi);
+#pragma unroll
+    for (int i = 7; i < 17; ++i) g[i] = 0.f;
+    if (method != 1) {
+        const f3 x = u.x;
+        const f3 y = mk3(S[0] * x.x + S[1] * x.y + S[2] * x.z, S[3] * x.x + S[4] * x.y + S[5] * x.z, S[6] * x.x + S[7] * x.y + S[8] * x.z);
+        const f3 gl = w * u.dx_l;
+        dtr = dtr + gl;
+        float4 dq_act;
+        qact_bwd(q, y, gl, dq_act);
+        dq = dq + dq_act;
+        // dy = R(q)^T g ; for the (generally unit) q the transpose action is act(conj(q), g) only when |q|=1,
+        // so use the exact adjoint of p -> p + 2w(v x p) + 2 v x (v x p): g + 2w (g x v) + 2 (v x (v x g))
+        const f3 vq = vec(q);
+        const f3 dy = gl + 2.f * (q.w * cross(gl, vq) + cross(vq, cross(vq, gl)));
+        g[7] = dy.x * x.x; g[8] = dy.x * x.y; g[9] = dy.x * x.z;
+        g[10] = dy.y * x.x; g[11] = dy.y * x.y; g[12] = dy.y * x.z;
+        g[13] = dy.z * x.x; g[14] = dy.z * x.y; g[15] = dy.z * x.z;
+    }
+    if (method != 0) {
+        const float qq = dot4(q, q), inv = 1.f / sqrtf(qq);
+        const float4 qn = inv * q;
+        const float4 th = mkq(0.5f * tr, 0.f);
+        // qd = th (x) qn
+        const float4 gqd = w * u.dsq_d;
+        float4 dqn = w * u.dsq_r + qmul(qconj(th), gqd);
+        const float4 dth = qmul(gqd, qconj(qn));
+        dtr = dtr + 0.5f * vec(dth);
+        dq = dq + inv * (dqn + (-dot4(qn, dqn)) * qn);
+    }
+    if (method == 2) g[16] = w * u.dlam_raw;
+    g[0] = dtr.x; g[1] = dtr.y; g[2] = dtr.z;
+    g[3] = dq.x; g[4] = dq.y; g[5] = dq.z; g[6] = dq.w;
+}
+
+// Node-centric vertex backward (the default), two kernels:
+//   skin_vertex_upstream_kernel : one thread per (timestamp, vertex) computes the vertex's upstream gradients ONCE and
+//                                 stores them as 16 floats (64 B, four coalesced float4 stores);
+//   skin_node_backward_kernel   : one CTA per (node, timestamp, split) walks the node's incidence list
+//                                 (dm4d_skin_node_incidence: the (vertex, slot) pairs that reference the node, ascending),
+//                                 gathers the 64 B records, applies the node-dependent ~100 flops per incidence, sums the
+//                                 17 node gradients in registers and reduces them once per CTA.
+// With one split the result is a plain store: no atomics, no memset, bit-reproducible.
+__global__ void __launch_bounds__(DM4D_BLOCK) skin_vertex_upstream_kernel(SkinBwdK a, float4* __restrict__ up) {
+    const dm4d_skin_desc& d = a.d;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)d.n_t * d.V) return;
+    const int t = (int)(idx / d.V), v = (int)(idx - (long long)t * d.V);
+    VertUp u;
+    vertex_upstream(a, t, v, u);
+    float4* o = up + (size_t)idx * 4;
+    o[0] = make_float4(u.dxi.x, u.dxi.y, u.dxi.z, u.dlam_raw);
+    o[1] = make_float4(u.dx_l.x, u.dx_l.y, u.dx_l.z, 0.f);
+    o[2] = u.dsq_r;
+    o[3] = u.dsq_d;
+}
+
+__global__ void __launch_bounds__(DM4D_BLOCK) skin_node_backward_kernel(SkinBwdK a, const float4* __restrict__ up,
+                                                                        const int32_t* __restrict__ inc_ptr,
+                                                                        const int32_t* __restrict__ inc) {
+    __shared__ float part[DM4D_BLOCK / 32][17];
+    const dm4d_skin_desc& d = a.d;
+    const int n = blockIdx.x, t = blockIdx.y, K = d.K;
+    const size_t base = (size_t)t * d.M + n;
+    const f3 tr = ld3(d.node_trans + base * 3);
+    const float4 q = ldq(d.node_rot + base * 4);
+    const LogBwdCoef lc = so3_log_bwd_coef(q);
+    float S[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) S[i] = d.method != 1 ? d.node_scale[base * 9 + i] : 0.f;
+    float acc[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) acc[i] = 0.f;
+    const int lo = inc_ptr[n], hi = inc_ptr[n + 1];
+    const float4* upt = up + (size_t)t * d.V * 4;
+    for (int i = lo + blockIdx.z * blockDim.x + threadIdx.x; i < hi; i += gridDim.z * blockDim.x) {
+        const int e = inc[i];
+        const int v = e / K;
+        const float4 r0 = upt[(size_t)v * 4];
+        VertUp u;
+        u.dxi = mk3(r0.x, r0.y, r0.z); u.dlam_raw = r0.w;
+        u.x = mk3(0, 0, 0); u.dx_l = u.x;
+        u.dsq_r = make_float4(0, 0, 0, 0); u.dsq_d = u.dsq_r;
+        if (d.method != 1) {                               // the records' halves a method does not use are not read
+            const float4 r1 = upt[(size_t)v * 4 + 1];
+            u.dx_l = mk3(r1.x, r1.y, r1.z);
+            u.x = ld3(d.rest_verts + (size_t)v * 3);
+        }
+        if (d.method != 0) { u.dsq_r = upt[(size_t)v * 4 + 2]; u.dsq_d = upt[(size_t)v * 4 + 3]; }
+        float g[17];
+        incidence_gradient(d.method, d.nbr_w[e], u, tr, q, lc, S, g);
+#pragma unroll
+        for (int j = 0; j < 17; ++j) acc[j] += g[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 17; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int j = 0; j < 17; ++j) part[threadIdx.x >> 5][j] = acc[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 17) {
+        const int j = threadIdx.x;
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < DM4D_BLOCK / 32; ++w) tot += part[w][j];
+        float* dst;
+        if (j < 3) dst = a.dn_trans + base * 3 + j;
+        else if (j < 7) dst = a.dn_rot + base * 4 + (j - 3);
+        else if (j < 16) dst = a.dn_scale + base * 9 + (j - 7);
+        else dst = a.dn_opac + base;
+        if (gridDim.z == 1) *dst = tot;
+        else if (tot != 0.f) atomicAdd(dst, tot);
+    }
+}
+
+// Backward of one (timestamp, vertex) for callers without an incidence list: adds its contributions to the four
+// node-gradient tables of timestamp t (tT [M,3], tQ [M,4], tS [M,9], tO [M]) — global memory, or a per-CTA copy in
+// shared memory.
+__device__ __forceinline__ void vertex_backward(const SkinBwdK& a, int t, int v, float* tT, float* tQ, float* tS, float* tO) {
+    const dm4d_skin_desc& d = a.d;
+    VertUp u;
+    vertex_upstream(a, t, v, u);
     for (int k = 0; k < d.K; ++k) {
         const int n = d.nbr_idx[(size_t)v * d.K + k];
         const float w = d.nbr_w[(size_t)v * d.K + k];
         const size_t base = (size_t)t * d.M + n;
-        const f3 tr = ld3(d.node_trans + base * 3);
+        float g[17];
         const float4 q = ldq(d.node_rot + base * 4);
-        f3 dtr = mk3(0, 0, 0);
-        float4 dq = so3_log_bwd(q, w * dxi);
+        incidence_gradient(d.method, w, u, ld3(d.node_trans + base * 3), q, so3_log_bwd_coef(q),
+                           d.method != 1 ? d.node_scale + base * 9 : nullptr, g);
         if (d.method != 1) {
-            const float* S = d.node_scale + base * 9;
-            const f3 y = mk3(S[0] * x.x + S[1] * x.y + S[2] * x.z, S[3] * x.x + S[4] * x.y + S[5] * x.z, S[6] * x.x + S[7] * x.y + S[8] * x.z);
-            const f3 g = w * dx_l;
-            dtr = dtr + g;
-            float4 dq_act;
-            qact_bwd(q, y, g, dq_act);
-            dq = dq + dq_act;
-            // dy = R(q)^T g ; for the (generally unit) q the transpose action is act(conj(q), g) only when |q|=1,
-            // so use the exact adjoint of p -> p + 2w(v x p) + 2 v x (v x p): g + 2w (g x v) + 2 (v x (v x g))
-            const f3 vq = vec(q);
-            const f3 dy = g + 2.f * (q.w * cross(g, vq) + cross(vq, cross(vq, g)));
-            float* dS = tS + (size_t)n * 9;
-            atomicAdd(dS + 0, dy.x * x.x); atomicAdd(dS + 1, dy.x * x.y); atomicAdd(dS + 2, dy.x * x.z);
-            atomicAdd(dS + 3, dy.y * x.x); atomicAdd(dS + 4, dy.y * x.y); atomicAdd(dS + 5, dy.y * x.z);
-            atomicAdd(dS + 6, dy.z * x.x); atomicAdd(dS + 7, dy.z * x.y); atomicAdd(dS + 8, dy.z * x.z);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) atomicAdd(tS + (size_t)n * 9 + i, g[7 + i]);
         }
-        if (d.method != 0) {
-            const float qq = dot4(q, q), inv = 1.f / sqrtf(qq);
-            const float4 qn = inv * q;
-            const float4 th = mkq(0.5f * tr, 0.f);
-            // qd = th (x) qn
-            const float4 gqd = w * dsq_d;
-            float4 dqn = w * dsq_r + qmul(qconj(th), gqd);
-            const float4 dth = qmul(gqd, qconj(qn));
-            dtr = dtr + 0.5f * vec(dth);
-            dq = dq + inv * (dqn + (-dot4(qn, dqn)) * qn);
-        }
-        if (d.method == 2) atomicAdd(tO + n, w * dlam_raw);
-        float* dT = tT + (size_t)n * 3;
-        atomicAdd(dT + 0, dtr.x); atomicAdd(dT + 1, dtr.y); atomicAdd(dT + 2, dtr.z);
-        float* dQ = tQ + (size_t)n * 4;
-        atomicAdd(dQ + 0, dq.x); atomicAdd(dQ + 1, dq.y); atomicAdd(dQ + 2, dq.z); atomicAdd(dQ + 3, dq.w);
+        if (d.method == 2) atomicAdd(tO + n, g[16]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) atomicAdd(tT + (size_t)n * 3 + i, g[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) atomicAdd(tQ + (size_t)n * 4 + i, g[3 + i]);
     }
 }
 
@@ -283,10 +403,8 @@ __global__ void __launch_bounds__(DM4D_BLOCK) skin_vertex_backward_kernel(SkinBw
     vertex_backward(a, t, v, a.dn_trans + tb * 3, a.dn_rot + tb * 4, a.dn_scale + tb * 9, a.dn_opac + tb);
 }
 
-// Node-gradient tables of ONE timestamp accumulated in shared memory (M x 17 floats: 68 KB at M = 1000): a vertex adds
-// to its K nodes with shared-memory atomics — a block's vertices are mesh-neighbours and share a few dozen nodes, which
-// in global memory meant 13.6 M atomics on 8.7 k addresses at C5 (0.38 ms of the 0.45 ms skinning fwd+bwd) — and the
-// CTA flushes its non-zero entries once.  grid = (CTAs per timestamp, n_t); every CTA walks its vertices grid-stride.
+// No incidence list given: node-gradient tables of ONE timestamp accumulated in shared memory (M x 17 floats), flushed
+// once per CTA.  grid = (CTAs per timestamp, n_t); every CTA walks its vertices grid-stride.
 __global__ void __launch_bounds__(DM4D_BLOCK) skin_vertex_backward_smem_kernel(SkinBwdK a) {
     extern __shared__ float tab[];
     const dm4d_skin_desc& d = a.d;
@@ -309,105 +427,251 @@ __global__ void __launch_bounds__(DM4D_BLOCK) skin_vertex_backward_smem_kernel(S
     }
 }
 
+// Incidence lists of the control nodes: inc_ptr [M+1], inc [V*K] = the flat indices e = v*K + k with nbr_idx[e] == n,
+// ascending inside every node (deterministic summation order).  Start-up only (the graph is fixed after
+// dynamic_sugar.py:745-861): a histogram, a one-CTA scan and one warp per node compacting in order.
+__global__ void __launch_bounds__(DM4D_BLOCK) incidence_count_kernel(const int32_t* nbr_idx, int n, int M, int32_t* count, int32_t* bad) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int node = nbr_idx[e];
+    if (node < 0 || node >= M) { *bad = 1; return; }
+    atomicAdd(count + node, 1);
+}
+__global__ void __launch_bounds__(1024) incidence_scan_kernel(const int32_t* count, int M, int32_t* inc_ptr) {
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b = 0; b < M; b += 1024) {
+        const int i = b + threadIdx.x;
+        const int32_t c = i < M ? count[i] : 0;
+        int32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += y; }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int32_t w = warp_tot[threadIdx.x], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, wi, o); if (threadIdx.x >= o) wi += y; }
+            warp_tot[threadIdx.x] = wi - w;
+        }
+        __syncthreads();
+        const int32_t excl = carry + warp_tot[threadIdx.x >> 5] + incl - c;
+        if (i < M) inc_ptr[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + c;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) inc_ptr[M] = carry;
+}
+__global__ void __launch_bounds__(DM4D_BLOCK) incidence_fill_kernel(const int32_t* nbr_idx, int n, int M, const int32_t* inc_ptr, int32_t* inc) {
+    const int node = blockIdx.x * (DM4D_BLOCK / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (node >= M) return;
+    int pos = inc_ptr[node];
+    for (int b = 0; b < n; b += 32) {
+        const int e = b + lane;
+        const bool hit = e < n && nbr_idx[e] == node;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) inc[pos + __popc(m & ((1u << lane) - 1u))] = e;
+        pos += __popc(m);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Gaussian stage: one thread per (timestamp, face)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 wxyz_to_xyzw(float4 q) { return make_float4(q.y, q.z, q.w, q.x); }
 __device__ __forceinline__ float4 xyzw_to_wxyz(float4 q) { return make_float4(q.w, q.x, q.y, q.z); }
 
-__global__ void __launch_bounds__(DM4D_BLOCK) skin_gaussian_forward_kernel(SkinK a) {
-    const dm4d_skin_desc& d = a.d;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)d.n_t * d.F) return;
-    const int t = (int)(idx / d.F), f = (int)(idx - (long long)t * d.F);
-    const int i0 = d.faces[(size_t)f * 3], i1 = d.faces[(size_t)f * 3 + 1], i2 = d.faces[(size_t)f * 3 + 2];
-    const size_t vb = (size_t)t * d.V;
-    const f3 x0 = ld3(a.verts + (vb + i0) * 3), x1 = ld3(a.verts + (vb + i1) * 3), x2 = ld3(a.verts + (vb + i2) * 3);
-    const f3 L0 = so3_log(ldq(a.vert_rot + (vb + i0) * 4));
-    const f3 L1 = so3_log(ldq(a.vert_rot + (vb + i1) * 4));
-    const f3 L2 = so3_log(ldq(a.vert_rot + (vb + i2) * 4));
-    f3 nrm = cross(x1 - x0, x2 - x0);
-    nrm = (1.f / fmaxf(sqrtf(dot(nrm, nrm)), 1e-6f)) * nrm;
-    nrm = (1.f / fmaxf(sqrtf(dot(nrm, nrm)), 1e-12f)) * nrm;
-    for (int j = 0; j < d.g; ++j) {
-        const float b0 = d.bary[j * 3], b1 = d.bary[j * 3 + 1], b2 = d.bary[j * 3 + 2];
-        const size_t gi = (size_t)t * a.P + (size_t)f * d.g + j;
-        st3(a.means + gi * 3, b0 * x0 + b1 * x1 + b2 * x2);
-        const float4 dq = so3_exp(b0 * L0 + b1 * L1 + b2 * L2);
-        const float4 rest = wxyz_to_xyzw(ldq(d.rest_quat + ((size_t)f * d.g + j) * 4));
-        float4 u = xyzw_to_wxyz(qmul(dq, rest));
-        const float inv = 1.f / fmaxf(sqrtf(dot4(u, u)), 1e-12f);
-        *reinterpret_cast<float4*>(a.rots + gi * 4) = inv * u;
-        if (a.normals) st3(a.normals + gi * 3, nrm);
+// Per-Gaussian arrays are [n_t*F*g, k] with k = 3 or 4: a thread owns the g*k consecutive floats of its face, so direct
+// accesses are stride-(g*k) scalars (32 sectors per request).  Instead every warp moves its 32 faces' block (32*g*k
+// contiguous floats) between global memory and a shared staging buffer with coalesced (16-byte when aligned) accesses.
+constexpr int STAGE_FLOATS = 32 * 6 * 4;
+
+__device__ __forceinline__ void warp_store_block(float* __restrict__ dst, const float* st, int n, int lane) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (n & 3) == 0) {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        const float4* s4 = reinterpret_cast<const float4*>(st);
+        for (int i = lane; i < n / 4; i += 32) d4[i] = s4[i];
+    } else {
+        for (int i = lane; i < n; i += 32) dst[i] = st[i];
+    }
+}
+__device__ __forceinline__ void warp_load_block(float* st, const float* __restrict__ src, int n, int lane) {
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (n & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(st);
+        for (int i = lane; i < n / 4; i += 32) d4[i] = s4[i];
+    } else {
+        for (int i = lane; i < n; i += 32) st[i] = src[i];
     }
 }
 
-__global__ void __launch_bounds__(DM4D_BLOCK) skin_gaussian_backward_kernel(SkinBwdK a) {
+__global__ void __launch_bounds__(DM4D_BLOCK) skin_gaussian_forward_kernel(SkinK a) {
+    __shared__ __align__(16) float stage_all[DM4D_BLOCK / 32][STAGE_FLOATS];
     const dm4d_skin_desc& d = a.d;
+    const int lane = threadIdx.x & 31, g = d.g;
+    float* st = stage_all[threadIdx.x >> 5];
+    const long long total = (long long)d.n_t * d.F;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)d.n_t * d.F) return;
-    const int t = (int)(idx / d.F), f = (int)(idx - (long long)t * d.F);
-    const int vi[3] = {d.faces[(size_t)f * 3], d.faces[(size_t)f * 3 + 1], d.faces[(size_t)f * 3 + 2]};
+    const long long wfirst = idx - lane;
+    if (wfirst >= total) return;
+    const int cnt = (int)min(32ll, total - wfirst);
+    const bool live = idx < total;
+    f3 x0 = mk3(0, 0, 0), x1 = x0, x2 = x0, L0 = x0, L1 = x0, L2 = x0, nrm = x0;
+    int f = 0;
+    if (live) {
+        const int t = (int)(idx / d.F);
+        f = (int)(idx - (long long)t * d.F);
+        const int i0 = d.faces[(size_t)f * 3], i1 = d.faces[(size_t)f * 3 + 1], i2 = d.faces[(size_t)f * 3 + 2];
+        const size_t vb = (size_t)t * d.V;
+        x0 = ld3(a.verts + (vb + i0) * 3); x1 = ld3(a.verts + (vb + i1) * 3); x2 = ld3(a.verts + (vb + i2) * 3);
+        L0 = so3_log(ldq(a.vert_rot + (vb + i0) * 4));
+        L1 = so3_log(ldq(a.vert_rot + (vb + i1) * 4));
+        L2 = so3_log(ldq(a.vert_rot + (vb + i2) * 4));
+        nrm = cross(x1 - x0, x2 - x0);
+        nrm = (1.f / fmaxf(sqrtf(dot(nrm, nrm)), 1e-6f)) * nrm;
+        nrm = (1.f / fmaxf(sqrtf(dot(nrm, nrm)), 1e-12f)) * nrm;
+    }
+    // rest quaternions of the warp's faces: [F*g,4], contiguous per warp unless the warp straddles two timestamps
+    const bool one_t = (wfirst / d.F) == ((wfirst + cnt - 1) / d.F);
+    if (one_t) {
+        warp_load_block(st, d.rest_quat + (size_t)(wfirst % d.F) * g * 4, cnt * g * 4, lane);
+        __syncwarp();
+    }
+    float4 rest[6];
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+            if (j < g) rest[j] = wxyz_to_xyzw(one_t ? *reinterpret_cast<const float4*>(st + (lane * g + j) * 4)
+                                                     : ldq(d.rest_quat + ((size_t)f * g + j) * 4));
+    }
+    __syncwarp();
+    // rotations
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            if (j >= g) break;
+            const float b0 = d.bary[j * 3], b1 = d.bary[j * 3 + 1], b2 = d.bary[j * 3 + 2];
+            const float4 dq = so3_exp(b0 * L0 + b1 * L1 + b2 * L2);
+            float4 u = xyzw_to_wxyz(qmul(dq, rest[j]));
+            const float inv = 1.f / fmaxf(sqrtf(dot4(u, u)), 1e-12f);
+            *reinterpret_cast<float4*>(st + (lane * g + j) * 4) = inv * u;
+        }
+    }
+    __syncwarp();
+    warp_store_block(a.rots + (size_t)wfirst * g * 4, st, cnt * g * 4, lane);
+    __syncwarp();
+    // means
+    if (live) {
+        for (int j = 0; j < g; ++j) {
+            const float b0 = d.bary[j * 3], b1 = d.bary[j * 3 + 1], b2 = d.bary[j * 3 + 2];
+            st3(st + (lane * g + j) * 3, b0 * x0 + b1 * x1 + b2 * x2);
+        }
+    }
+    __syncwarp();
+    warp_store_block(a.means + (size_t)wfirst * g * 3, st, cnt * g * 3, lane);
+    if (a.normals) {
+        __syncwarp();
+        if (live)
+            for (int j = 0; j < g; ++j) st3(st + (lane * g + j) * 3, nrm);
+        __syncwarp();
+        warp_store_block(a.normals + (size_t)wfirst * g * 3, st, cnt * g * 3, lane);
+    }
+}
+
+__global__ void __launch_bounds__(DM4D_BLOCK, 3) skin_gaussian_backward_kernel(SkinBwdK a) {
+    __shared__ __align__(16) float stage_all[DM4D_BLOCK / 32][STAGE_FLOATS];
+    const dm4d_skin_desc& d = a.d;
+    const int lane = threadIdx.x & 31, g = d.g;
+    float* st = stage_all[threadIdx.x >> 5];
+    const long long total = (long long)d.n_t * d.F;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long wfirst = idx - lane;
+    if (wfirst >= total) return;
+    const int cnt = (int)min(32ll, total - wfirst);
+    const bool live = idx < total;
+    const int t = live ? (int)(idx / d.F) : 0, f = live ? (int)(idx - (long long)t * d.F) : 0;
+    int vi[3] = {0, 0, 0};
     const size_t vb = (size_t)t * d.V;
     f3 x[3], L[3];
     float4 r[3];
-    for (int k = 0; k < 3; ++k) {
-        x[k] = ld3(a.verts + (vb + vi[k]) * 3);
-        r[k] = ldq(a.vert_rot + (vb + vi[k]) * 4);
-        L[k] = so3_log(r[k]);
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            vi[k] = d.faces[(size_t)f * 3 + k];
+            x[k] = ld3(a.verts + (vb + vi[k]) * 3);
+            r[k] = ldq(a.vert_rot + (vb + vi[k]) * 4);
+            L[k] = so3_log(r[k]);
+        }
     }
     f3 dx[3] = {mk3(0, 0, 0), mk3(0, 0, 0), mk3(0, 0, 0)};
     f3 dL[3] = {mk3(0, 0, 0), mk3(0, 0, 0), mk3(0, 0, 0)};
     f3 dn_sum = mk3(0, 0, 0);
-    for (int j = 0; j < d.g; ++j) {
-        const float b[3] = {d.bary[j * 3], d.bary[j * 3 + 1], d.bary[j * 3 + 2]};
-        const size_t gi = (size_t)t * a.P + (size_t)f * d.g + j;
-        if (a.g_means) {
-            const f3 gm = ld3(a.g_means + gi * 3);
-            for (int k = 0; k < 3; ++k) dx[k] = dx[k] + b[k] * gm;
-        }
-        if (a.g_rots) {
-            const f3 xi = b[0] * L[0] + b[1] * L[1] + b[2] * L[2];
-            const float4 dq = so3_exp(xi);
-            const float4 rest = wxyz_to_xyzw(ldq(d.rest_quat + ((size_t)f * d.g + j) * 4));
-            const float4 u = qmul(dq, rest);                         // xyzw
-            const float nu = fmaxf(sqrtf(dot4(u, u)), 1e-12f), inv = 1.f / nu;
-            const float4 qn = inv * u;
-            const float4 gq = wxyz_to_xyzw(ldq(a.g_rots + gi * 4));  // incoming gradient is wxyz
-            const float4 du = inv * (gq + (-dot4(qn, gq)) * qn);
-            const float4 ddq = qmul(du, qconj(rest));
-            const f3 dxi = so3_exp_bwd(xi, ddq);
-            for (int k = 0; k < 3; ++k) dL[k] = dL[k] + b[k] * dxi;
-        }
-        if (a.g_normals) dn_sum = dn_sum + ld3(a.g_normals + gi * 3);
+    if (a.g_means) {
+        warp_load_block(st, a.g_means + (size_t)wfirst * g * 3, cnt * g * 3, lane);
+        __syncwarp();
+        if (live)
+            for (int j = 0; j < g; ++j) {
+                const f3 gm = ld3(st + (lane * g + j) * 3);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) dx[k] = dx[k] + d.bary[j * 3 + k] * gm;
+            }
+        __syncwarp();
     }
+    if (a.g_normals) {
+        warp_load_block(st, a.g_normals + (size_t)wfirst * g * 3, cnt * g * 3, lane);
+        __syncwarp();
+        if (live)
+            for (int j = 0; j < g; ++j) dn_sum = dn_sum + ld3(st + (lane * g + j) * 3);
+        __syncwarp();
+    }
+    if (a.g_rots) {
+        warp_load_block(st, a.g_rots + (size_t)wfirst * g * 4, cnt * g * 4, lane);
+        __syncwarp();
+        if (live)
+            for (int j = 0; j < g; ++j) {
+                const float b[3] = {d.bary[j * 3], d.bary[j * 3 + 1], d.bary[j * 3 + 2]};
+                const f3 xi = b[0] * L[0] + b[1] * L[1] + b[2] * L[2];
+                const float4 dq = so3_exp(xi);
+                const float4 rest = wxyz_to_xyzw(ldq(d.rest_quat + ((size_t)f * g + j) * 4));
+                const float4 u = qmul(dq, rest);                         // xyzw
+                const float nu = fmaxf(sqrtf(dot4(u, u)), 1e-12f), inv = 1.f / nu;
+                const float4 qn = inv * u;
+                const float4 gq = wxyz_to_xyzw(*reinterpret_cast<const float4*>(st + (lane * g + j) * 4));  // incoming gradient is wxyz
+                const float4 du = inv * (gq + (-dot4(qn, gq)) * qn);
+                const float4 ddq = qmul(du, qconj(rest));
+                const f3 dxi = so3_exp_bwd(xi, ddq);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) dL[k] = dL[k] + b[k] * dxi;
+            }
+    }
+    if (!live) return;
     if (a.g_normals) {
         const f3 e1 = x[1] - x[0], e2 = x[2] - x[0];
         const f3 c = cross(e1, e2);
         const float len = sqrtf(dot(c, c));
+        // regular branch: n = c/|c|; clamped branch: n = c / 1e-6 (then re-normalised) -> gradient of the unnormalised direction
+        f3 dc;
         if (len > 1e-6f) {
             const f3 n = (1.f / len) * c;
-            const f3 dc = (1.f / len) * (dn_sum - dot(n, dn_sum) * n);
-            const f3 de1 = cross(e2, dc), de2 = cross(dc, e1);
-            dx[0] = dx[0] - (de1 + de2);
-            dx[1] = dx[1] + de1;
-            dx[2] = dx[2] + de2;
+            dc = (1.f / len) * (dn_sum - dot(n, dn_sum) * n);
         } else {
-            // clamped branch: n = c / 1e-6 (then re-normalised); gradient of the unnormalised direction
-            const f3 dc = 1e6f * dn_sum;
-            const f3 de1 = cross(e2, dc), de2 = cross(dc, e1);
-            dx[0] = dx[0] - (de1 + de2);
-            dx[1] = dx[1] + de1;
-            dx[2] = dx[2] + de2;
+            dc = 1e6f * dn_sum;
         }
+        const f3 de1 = cross(e2, dc), de2 = cross(dc, e1);
+        dx[0] = dx[0] - (de1 + de2);
+        dx[1] = dx[1] + de1;
+        dx[2] = dx[2] + de2;
     }
+    // one 16-byte vector reduction per corner and quantity (the scratch rows are padded to float4)
+#pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float* pv = a.dverts + (vb + vi[k]) * 3;
-        atomicAdd(pv + 0, dx[k].x); atomicAdd(pv + 1, dx[k].y); atomicAdd(pv + 2, dx[k].z);
+        red_add_v4(a.dverts + (vb + vi[k]) * 4, dx[k].x, dx[k].y, dx[k].z, 0.f);
         if (a.g_rots) {
             const float4 dr = so3_log_bwd(r[k], dL[k]);
-            float* pr = a.dvert_rot + (vb + vi[k]) * 4;
-            atomicAdd(pr + 0, dr.x); atomicAdd(pr + 1, dr.y); atomicAdd(pr + 2, dr.z); atomicAdd(pr + 3, dr.w);
+            red_add_v4(a.dvert_rot + (vb + vi[k]) * 4, dr.x, dr.y, dr.z, dr.w);
         }
     }
 }
@@ -596,29 +860,45 @@ extern "C" int dm4d_skin_backward(const dm4d_skin_desc* d, const float* verts, c
     }
     cudaStream_t s = (cudaStream_t)stream;
     const size_t nv = (size_t)d->n_t * d->V, nf = (size_t)d->n_t * d->F, nm = (size_t)d->n_t * d->M;
-    if (dL_dverts_in) DM4D_CUDA_CHECK(cudaMemcpyAsync(dverts, dL_dverts_in, nv * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    else DM4D_CUDA_CHECK(cudaMemsetAsync(dverts, 0, nv * 3 * sizeof(float), s));
-    if (dL_dvert_rot_in) DM4D_CUDA_CHECK(cudaMemcpyAsync(dvert_rot, dL_dvert_rot_in, nv * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    else DM4D_CUDA_CHECK(cudaMemsetAsync(dvert_rot, 0, nv * 4 * sizeof(float), s));
-    DM4D_CUDA_CHECK(cudaMemsetAsync(dL_dnode_trans, 0, nm * 3 * sizeof(float), s));
-    DM4D_CUDA_CHECK(cudaMemsetAsync(dL_dnode_rot, 0, nm * 4 * sizeof(float), s));
-    DM4D_CUDA_CHECK(cudaMemsetAsync(dL_dnode_scale, 0, nm * 9 * sizeof(float), s));
-    DM4D_CUDA_CHECK(cudaMemsetAsync(dL_dnode_opacity, 0, nm * sizeof(float), s));
+    if ((reinterpret_cast<uintptr_t>(dverts) | reinterpret_cast<uintptr_t>(dvert_rot)) & 15) {
+        dm4d_set_error("skin backward: dverts / dvert_rot must be 16-byte aligned");
+        return DM4D_EINVAL;
+    }
+    DM4D_CUDA_CHECK(cudaMemsetAsync(dverts, 0, nv * 4 * sizeof(float), s));
+    DM4D_CUDA_CHECK(cudaMemsetAsync(dvert_rot, 0, nv * 4 * sizeof(float), s));
     SkinBwdK a;
     a.d = *d; a.P = d->F * d->g;
     a.verts = verts; a.vert_rot = vert_rot;
     a.g_means = dL_dmeans3D; a.g_rots = dL_drotations; a.g_normals = dL_dnormals;
     a.dverts = dverts; a.dvert_rot = dvert_rot;
+    a.dverts_in = dL_dverts_in; a.dvert_rot_in = dL_dvert_rot_in;
     a.dn_trans = dL_dnode_trans; a.dn_rot = dL_dnode_rot; a.dn_scale = dL_dnode_scale; a.dn_opac = dL_dnode_opacity;
     if (dL_dmeans3D || dL_drotations || dL_dnormals) {
         KernelTimer kt(DM4D_K_SKIN_GAUSS_BWD, s);
         skin_gaussian_backward_kernel<<<(unsigned)((nf + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(a);
     }
     DM4D_CUDA_CHECK(cudaGetLastError());
+    // enough CTAs to fill the GPU: the node lists are split when nodes x timestamps alone would not
+    if ((d->node_inc_ptr != nullptr) != (d->node_inc != nullptr) || (d->node_inc && !d->vert_scratch)) {
+        dm4d_set_error("skin backward: node_inc_ptr, node_inc and vert_scratch go together");
+        return DM4D_EINVAL;
+    }
+    const int splits = d->node_inc ? std::max(1, std::min(16, (148 * 8 + d->M * d->n_t - 1) / (d->M * d->n_t))) : 0;
+    if (splits != 1) {
+        DM4D_CUDA_CHECK(cudaMemsetAsync(dL_dnode_trans, 0, nm * 3 * sizeof(float), s));
+        DM4D_CUDA_CHECK(cudaMemsetAsync(dL_dnode_rot, 0, nm * 4 * sizeof(float), s));
+        DM4D_CUDA_CHECK(cudaMemsetAsync(dL_dnode_scale, 0, nm * 9 * sizeof(float), s));
+        DM4D_CUDA_CHECK(cudaMemsetAsync(dL_dnode_opacity, 0, nm * sizeof(float), s));
+    }
     {
         KernelTimer kt(DM4D_K_SKIN_VERT_BWD, s);
         const size_t tab_bytes = (size_t)d->M * 17 * sizeof(float);
-        if (tab_bytes <= 200 * 1024) {
+        if (splits) {
+            if (d->n_t > 65535) { dm4d_set_error("skin backward: n_t > 65535"); return DM4D_EINVAL; }
+            float4* up = reinterpret_cast<float4*>(d->vert_scratch);
+            skin_vertex_upstream_kernel<<<(unsigned)((nv + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(a, up);
+            skin_node_backward_kernel<<<dim3((unsigned)d->M, (unsigned)d->n_t, (unsigned)splits), DM4D_BLOCK, 0, s>>>(a, up, d->node_inc_ptr, d->node_inc);
+        } else if (tab_bytes <= 200 * 1024) {
             static bool configured = false;
             if (!configured) {
                 DM4D_CUDA_CHECK(cudaFuncSetAttribute(skin_vertex_backward_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -631,6 +911,23 @@ extern "C" int dm4d_skin_backward(const dm4d_skin_desc* d, const float* verts, c
             skin_vertex_backward_kernel<<<(unsigned)((nv + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(a);
         }
     }
+    DM4D_CUDA_CHECK(cudaGetLastError());
+    return DM4D_OK;
+}
+
+extern "C" int dm4d_skin_node_incidence(const int32_t* nbr_idx, int32_t V, int32_t K, int32_t M, int32_t* inc_ptr,
+                                        int32_t* inc, int32_t* scratch, void* stream) {
+    if (!nbr_idx || !inc_ptr || !inc || !scratch || V <= 0 || K <= 0 || M <= 0 || (long long)V * K > 0x7fffffffLL) {
+        dm4d_set_error("dm4d_skin_node_incidence: bad argument");
+        return DM4D_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = V * K;
+    DM4D_CUDA_CHECK(cudaMemsetAsync(scratch, 0, ((size_t)M + 1) * sizeof(int32_t), s));
+    incidence_count_kernel<<<(n + DM4D_BLOCK - 1) / DM4D_BLOCK, DM4D_BLOCK, 0, s>>>(nbr_idx, n, M, scratch, scratch + M);
+    incidence_scan_kernel<<<1, 1024, 0, s>>>(scratch, M, inc_ptr);
+    const int per = DM4D_BLOCK / 32;
+    incidence_fill_kernel<<<(M + per - 1) / per, DM4D_BLOCK, 0, s>>>(nbr_idx, n, M, inc_ptr, inc);
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }

@@ -21,6 +21,35 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
 
+_INCIDENCE: dict = {}
+USE_NODE_INCIDENCE = True     # False: the C ABI's list-free backward (per-CTA node tables, shared-memory atomics)
+
+
+def node_incidence(nbr_idx: torch.Tensor, M: int):
+    """Incidence lists of the control nodes (``dm4d_skin_node_incidence``): ``inc_ptr`` [M+1], ``inc`` [V*K] int32.
+    The deformation graph is fixed after start-up (dynamic_sugar.py:745-861), so the lists are built once per
+    ``nbr_idx`` tensor (keyed on storage and version) and re-used by every backward."""
+    key = (nbr_idx.data_ptr(), nbr_idx._version, tuple(nbr_idx.shape), M, nbr_idx.device)
+    hit = _INCIDENCE.get(key)
+    if hit is not None:
+        return hit[0], hit[1]
+    if torch.cuda.is_current_stream_capturing():
+        raise _lib.Dm4dError("skinning: build the node incidence lists (one eager call) before capturing a CUDA graph")
+    V, K = nbr_idx.shape
+    dev = nbr_idx.device
+    inc_ptr = torch.empty(M + 1, dtype=torch.int32, device=dev)
+    inc = torch.empty(V * K, dtype=torch.int32, device=dev)
+    scratch = torch.empty(M + 1, dtype=torch.int32, device=dev)
+    check(_lib.lib().dm4d_skin_node_incidence(ptr(nbr_idx), V, K, M, ptr(inc_ptr), ptr(inc), ptr(scratch),
+                                              torch.cuda.current_stream().cuda_stream), "dm4d_skin_node_incidence")
+    if int(scratch[M]) != 0:
+        raise ValueError(f"nbr_idx holds node indices outside [0, {M})")
+    if len(_INCIDENCE) > 16:
+        _INCIDENCE.clear()
+    _INCIDENCE[key] = (inc_ptr, inc, nbr_idx)     # keeps nbr_idx alive: data_ptr stays unique
+    return inc_ptr, inc
+
+
 class _SkinFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, node_trans, node_rot, node_scale, node_opacity, rest_verts, faces, nbr_idx, nbr_w, bary,
@@ -49,6 +78,10 @@ class _SkinFunction(torch.autograd.Function):
                 _f32(rest_quat), nt, nr, ns, no]
         (d.rest_verts, d.faces, d.nbr_idx, d.nbr_w, d.bary, d.rest_quat, d.node_trans, d.node_rot, d.node_scale,
          d.node_opacity) = [ptr(t) for t in keep]
+        if USE_NODE_INCIDENCE and any(ctx.needs_input_grad[:4]):
+            inc_ptr, inc = node_incidence(keep[2], M)
+            d.node_inc_ptr, d.node_inc = ptr(inc_ptr), ptr(inc)
+            keep += [inc_ptr, inc]
         f32 = dict(dtype=torch.float32, device=dev)
         verts = torch.empty(T, V, 3, **f32)
         vert_rot = torch.empty(T, V, 4, **f32)
@@ -77,12 +110,15 @@ class _SkinFunction(torch.autograd.Function):
         g_means, g_rots, g_verts, g_vert_rot = c(g_means), c(g_rots), c(g_verts), c(g_vert_rot)
         g_normals = c(g_normals) if ctx.want_normals else None
         T, V, M = d.n_t, d.V, d.M
-        dverts = torch.empty(T, V, 3, **f32)
+        dverts = torch.empty(T, V, 4, **f32)
         dvrot = torch.empty(T, V, 4, **f32)
         dn_t = torch.empty(T, M, 3, **f32)
         dn_r = torch.empty(T, M, 4, **f32)
         dn_s = torch.empty(T, M, 9, **f32)
         dn_o = torch.empty(T, M, **f32)
+        if d.node_inc:
+            scratch = torch.empty(T, V, 16, **f32)
+            d.vert_scratch = ptr(scratch)
         check(l.dm4d_skin_backward(ctypes.byref(d), ptr(verts), ptr(vert_rot), ptr(g_means), ptr(g_rots),
                                    ptr(g_normals), ptr(g_verts), ptr(g_vert_rot), ptr(dverts), ptr(dvrot), ptr(dn_t),
                                    ptr(dn_r), ptr(dn_s), ptr(dn_o), torch.cuda.current_stream().cuda_stream),

@@ -173,7 +173,20 @@ typedef struct dm4d_skin_desc {
     const float* node_rot;     /* [n_t, M, 4] xyzw, unit */
     const float* node_scale;   /* [n_t, M, 9] row-major 3x3 (I + strain) */
     const float* node_opacity; /* [n_t, M]    sigmoid'ed lbs weight */
+    /* Optional (backward only; all three or none): the control nodes' incidence lists from dm4d_skin_node_incidence
+     * and a scratch buffer.  With them the vertex backward runs node-centric: upstream gradients once per vertex into
+     * vert_scratch, then one CTA per (node, timestamp) gathers its incidences (no atomics, bit-reproducible when
+     * M * n_t >= 1184).  Without them it accumulates per-CTA node tables with shared-memory atomics. */
+    const int32_t* node_inc_ptr; /* [M+1] */
+    const int32_t* node_inc;     /* [V*K] flat (vertex, slot) indices e = v*K + k, grouped by node, ascending */
+    float* vert_scratch;         /* [n_t, V, 16] caller-owned scratch, 16-byte aligned (overwritten) */
 } dm4d_skin_desc;
+
+/* Incidence lists of the deformation graph (start-up; the graph of dynamic_sugar.py:745-861 is fixed afterwards):
+ * inc_ptr [M+1], inc [V*K] as described above.  scratch: [M+1] int32; scratch[M] != 0 afterwards means that nbr_idx
+ * held an index outside [0, M) (the lists are then incomplete). */
+int dm4d_skin_node_incidence(const int32_t* nbr_idx, int32_t V, int32_t K, int32_t M, int32_t* inc_ptr, int32_t* inc,
+                             int32_t* scratch, void* stream);
 
 /* Outputs: verts [n_t,V,3], vert_rot [n_t,V,4] xyzw, means3D [n_t,P,3], rotations [n_t,P,4] wxyz
  * (normalised), normals [n_t,P,3] (deformed unit face normal repeated g times; may be NULL). */
@@ -183,7 +196,7 @@ int dm4d_skin_forward(const dm4d_skin_desc* d, float* verts, float* vert_rot, fl
 /* Backward: incoming dL_dmeans3D [n_t,P,3], dL_drotations [n_t,P,4], dL_dnormals [n_t,P,3] (any may
  * be NULL), plus optional direct gradients on the deformed vertices dL_dverts_in [n_t,V,3] and vertex
  * rotations dL_dvert_rot_in [n_t,V,4] (ARAP / mesh regularisers).  `verts`/`vert_rot` are the forward
- * outputs.  Scratch: dverts [n_t,V,3] and dvert_rot [n_t,V,4] (caller-owned, overwritten).
+ * outputs.  Scratch: dverts [n_t,V,4] (xyz + pad) and dvert_rot [n_t,V,4] (caller-owned, 16-byte aligned, overwritten).
  * Outputs (overwritten): dL_dnode_trans [n_t,M,3], dL_dnode_rot [n_t,M,4], dL_dnode_scale [n_t,M,9],
  * dL_dnode_opacity [n_t,M].  Exact Euclidean gradients of the forward formulas. */
 int dm4d_skin_backward(const dm4d_skin_desc* d, const float* verts, const float* vert_rot,
