@@ -95,6 +95,8 @@ SIGNATURES = {
     "dm4d_profile_collect": (ctypes.c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
     "dm4d_kernel_name": (c_char_p, [ctypes.c_int]),
     "dm4d_last_error": (c_char_p, []),
+    "dm4d_bias_residual_add_nhwc": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "dm4d_geglu": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "dm4d_version": (ctypes.c_int, []),
 }
 

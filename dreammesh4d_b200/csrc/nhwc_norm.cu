@@ -11,6 +11,7 @@
 // Two launches each way: (1) per-(sample, pixel-slab) partial sums -> [N,G,2] with one atomic per (block, group);
 // (2) element-wise apply with 8- / 16-byte vector accesses.  HBM-bound: forward reads x twice and writes y once.
 // Backward (weights are frozen in the SDS step: no dgamma / dbeta) needs the two group sums of dz*gamma and dz*gamma*xhat.
+#include <algorithm>
 #include <cuda_fp16.h>
 #include "raster_internal.cuh"
 
@@ -227,7 +228,81 @@ int backward_t(const NormArgs& a, int threads, dim3 grid, const void* x, const f
     return DM4D_OK;
 }
 
+// ---- convolution epilogues the library calls do not fuse ------------------------------------------------------------
+// out[m, c] = h[m, c] + bias[c] (+ res[m, c]): the bias of a cuDNN convolution (PyTorch adds it in a separate broadcast
+// pass over the output) folded into the residual add of the ResBlock that follows it (openaimodel.py:289,
+// model.py:138) — one pass instead of two.  Grid-stride over 4-channel vectors.
+template <typename T>
+__global__ void __launch_bounds__(256) bias_residual_kernel(long long nvec, int cvec, const T* __restrict__ h,
+                                                            const T* __restrict__ res, const float* __restrict__ bias,
+                                                            T* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cvec) * VEC;
+        float v[VEC], r[VEC];
+        Vec4<T>::load(h + i * VEC, v);
+        const float4 b = *reinterpret_cast<const float4*>(bias + c0);
+        v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+        if (res) {
+            Vec4<T>::load(res + i * VEC, r);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) v[j] += r[j];
+        }
+        Vec4<T>::store(out + i * VEC, v);
+    }
+}
+
+// GEGLU of the transformer feed-forward (attention.py:37-65): proj [M, 2D] -> out[m, d] = proj[m, d] * gelu(proj[m, D + d])
+// with the exact (erf) GELU; eager PyTorch runs chunk -> gelu -> mul as two passes over strided halves.
+template <typename T>
+__global__ void __launch_bounds__(256) geglu_kernel(long long nvec, int dvec, const T* __restrict__ proj, T* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / dvec;
+        const int d0 = (int)(i - m * dvec) * VEC;
+        const T* row = proj + m * (2ll * dvec * VEC);
+        float a[VEC], g[VEC];
+        Vec4<T>::load(row + d0, a);
+        Vec4<T>::load(row + (size_t)dvec * VEC + d0, g);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) a[j] *= 0.5f * g[j] * (1.0f + erff(g[j] * 0.70710678118654752f));
+        Vec4<T>::store(out + i * VEC, a);
+    }
+}
+
+template <typename T>
+int launch_bias_residual(long long M, int C, const void* h, const void* res, const float* bias, void* out, cudaStream_t s) {
+    const long long nvec = M * (C / VEC);
+    const unsigned blocks = (unsigned)std::min<long long>((nvec + 255) / 256, 148ll * 16);
+    bias_residual_kernel<T><<<blocks, 256, 0, s>>>(nvec, C / VEC, (const T*)h, (const T*)res, bias, (T*)out);
+    DM4D_CUDA_CHECK(cudaGetLastError());
+    return DM4D_OK;
+}
+template <typename T>
+int launch_geglu(long long M, int D, const void* proj, void* out, cudaStream_t s) {
+    const long long nvec = M * (D / VEC);
+    const unsigned blocks = (unsigned)std::min<long long>((nvec + 255) / 256, 148ll * 16);
+    geglu_kernel<T><<<blocks, 256, 0, s>>>(nvec, D / VEC, (const T*)proj, (T*)out);
+    DM4D_CUDA_CHECK(cudaGetLastError());
+    return DM4D_OK;
+}
+
 }  // namespace
+
+extern "C" int dm4d_bias_residual_add_nhwc(const void* h, const void* residual, const float* bias, int64_t M, int32_t C,
+                                           int32_t dtype, void* out, void* stream) {
+    if (!h || !bias || !out || M <= 0 || C <= 0 || C % VEC) { dm4d_set_error("dm4d_bias_residual_add_nhwc: bad argument (C must be a multiple of 4)"); return DM4D_EINVAL; }
+    if (dtype == DM4D_F16) return launch_bias_residual<__half>(M, C, h, residual, bias, out, (cudaStream_t)stream);
+    if (dtype == DM4D_F32) return launch_bias_residual<float>(M, C, h, residual, bias, out, (cudaStream_t)stream);
+    dm4d_set_error("dm4d_bias_residual_add_nhwc: dtype must be DM4D_F16 or DM4D_F32");
+    return DM4D_EINVAL;
+}
+
+extern "C" int dm4d_geglu(const void* proj, int64_t M, int32_t D, int32_t dtype, void* out, void* stream) {
+    if (!proj || !out || M <= 0 || D <= 0 || D % VEC) { dm4d_set_error("dm4d_geglu: bad argument (D must be a multiple of 4)"); return DM4D_EINVAL; }
+    if (dtype == DM4D_F16) return launch_geglu<__half>(M, D, proj, out, (cudaStream_t)stream);
+    if (dtype == DM4D_F32) return launch_geglu<float>(M, D, proj, out, (cudaStream_t)stream);
+    dm4d_set_error("dm4d_geglu: dtype must be DM4D_F16 or DM4D_F32");
+    return DM4D_EINVAL;
+}
 
 extern "C" int dm4d_groupnorm_nhwc_forward(const void* x, const float* chan_bias, const float* gamma, const float* beta,
                                            int32_t N, int32_t HW, int32_t C, int32_t G, float eps, int32_t silu,

@@ -86,3 +86,65 @@ class GroupNormAct(nn.GroupNorm):
             x = x + chan_bias.to(x.dtype)[:, :, None, None]
         y = F.group_norm(x, self.num_groups, self.weight, self.bias, self.eps)
         return F.silu(y) if self.silu else y
+
+
+class _BiasResidualNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, residual, bias32):
+        N, C, H, W = h.shape
+        h = h.contiguous(memory_format=torch.channels_last)
+        r = None if residual is None else residual.to(h.dtype).contiguous(memory_format=torch.channels_last)
+        out = torch.empty_like(h, memory_format=torch.channels_last)
+        check(_lib.lib().dm4d_bias_residual_add_nhwc(ptr(h), ptr(r), ptr(bias32), N * H * W, C, _DTYPES[h.dtype], ptr(out),
+                                                     torch.cuda.current_stream().cuda_stream), "dm4d_bias_residual_add_nhwc")
+        ctx.has_res = residual is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, (g if ctx.has_res else None), None
+
+
+def conv_nobias(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    """The convolution WITHOUT its bias: PyTorch adds a cuDNN convolution's bias in a separate broadcast pass over the
+    output; the callers fold it into the next fused pass instead (GroupNorm's channel bias, or ``bias_residual_add``)."""
+    return F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+
+def bias_residual_add(h: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``h + bias[None, :, None, None] (+ residual)`` in one channels-last pass (bias frozen: no gradient)."""
+    if bias is None:
+        return h if residual is None else residual + h
+    if h.is_cuda and h.dtype in _DTYPES and h.shape[1] % 4 == 0 and not bias.requires_grad:
+        return _BiasResidualNHWC.apply(h, residual, bias.detach().float().contiguous())
+    out = h + bias.to(h.dtype)[None, :, None, None]
+    return out if residual is None else residual + out
+
+
+class _GEGLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, proj):
+        D = proj.shape[-1] // 2
+        p2 = proj.contiguous()
+        out = torch.empty(*proj.shape[:-1], D, dtype=proj.dtype, device=proj.device)
+        check(_lib.lib().dm4d_geglu(ptr(p2), p2.numel() // (2 * D), D, _DTYPES[proj.dtype], ptr(out),
+                                    torch.cuda.current_stream().cuda_stream), "dm4d_geglu")
+        ctx.save_for_backward(p2)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (proj,) = ctx.saved_tensors      # the UNet runs without gradient in the SDS step; kept for completeness
+        with torch.enable_grad():
+            p = proj.detach().requires_grad_(True)
+            a, gate = p.chunk(2, dim=-1)
+            (a * F.gelu(gate)).backward(g)
+        return p.grad
+
+
+def geglu(proj: torch.Tensor) -> torch.Tensor:
+    """``a * gelu(gate)`` for ``a, gate = proj.chunk(2, -1)`` (attention.py:37-65), one pass on CUDA."""
+    if proj.is_cuda and proj.dtype in _DTYPES and proj.shape[-1] % 8 == 0:
+        return _GEGLU.apply(proj)
+    a, gate = proj.chunk(2, dim=-1)
+    return a * F.gelu(gate)

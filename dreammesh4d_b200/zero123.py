@@ -32,7 +32,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .nhwc import GroupNormAct
+from .nhwc import GroupNormAct, bias_residual_add, conv_nobias, geglu
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -118,9 +118,18 @@ class TimeResBlock(nn.Module):
     def forward(self, x: torch.Tensor, act_emb: torch.Tensor) -> torch.Tensor:
         """``act_emb`` = SiLU(time embedding), computed once per network evaluation by the caller.  Norm + SiLU (and the
         time-embedding add in front of the second norm) are one fused channels-last pass each (nhwc.py)."""
-        h = self.in_layers[2](self.in_layers[0](x))
-        h = self.out_layers[3](self.out_layers[0](h, chan_bias=self.emb_layers[1](act_emb)))
-        return self.skip_connection(x) + h
+        # convolution biases ride along with the next fused pass: the first with the time embedding into the second
+        # norm's channel bias, the second (plus a 1x1 skip's own) into the residual add
+        c1, c2 = self.in_layers[2], self.out_layers[3]
+        h = conv_nobias(c1, self.in_layers[0](x))
+        emb = self.emb_layers[1](act_emb)
+        h = conv_nobias(c2, self.out_layers[0](h, chan_bias=emb if c1.bias is None else emb + c1.bias))
+        if isinstance(self.skip_connection, nn.Identity):
+            return bias_residual_add(h, c2.bias, x)
+        sk = self.skip_connection
+        bias = sk.bias if c2.bias is None else (c2.bias if sk.bias is None else sk.bias + c2.bias)
+        xs = x.contiguous(memory_format=torch.channels_last)
+        return _nchw(F.linear(_nhwc(xs), sk.weight.flatten(1), bias)) + h
 
 
 class Attention(nn.Module):
@@ -159,8 +168,7 @@ class GatedFeedForward(nn.Module):
         self.net = Slots({0: proj, 2: nn.Linear(dim * 4, dim)})
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        a, gate = self.net[0].proj(x).chunk(2, dim=-1)
-        return self.net[2](a * F.gelu(gate))
+        return self.net[2](geglu(self.net[0].proj(x)))
 
 
 class TransformerBlock(nn.Module):
@@ -324,9 +332,15 @@ class VAEResBlock(nn.Module):
             self.nin_shortcut = nn.Conv2d(cin, cout, 1)
 
     def forward(self, x):
-        h = self.conv1(self.norm1(x))
-        h = self.conv2(self.norm2(h))
-        return (self.nin_shortcut(x) if hasattr(self, "nin_shortcut") else x) + h
+        # biases folded as in TimeResBlock
+        h = conv_nobias(self.conv1, self.norm1(x))
+        cb = None if self.conv1.bias is None else self.conv1.bias[None].expand(x.shape[0], -1)
+        h = conv_nobias(self.conv2, self.norm2(h, chan_bias=cb))
+        if not hasattr(self, "nin_shortcut"):
+            return bias_residual_add(h, self.conv2.bias, x)
+        sk = self.nin_shortcut
+        xs = x.contiguous(memory_format=torch.channels_last)
+        return _nchw(F.linear(_nhwc(xs), sk.weight.flatten(1), sk.bias + self.conv2.bias)) + h
 
 
 class VAEAttention(nn.Module):
@@ -340,8 +354,12 @@ class VAEAttention(nn.Module):
     def forward(self, x):
         B, C, H, W = x.shape
         h = _nhwc(self.norm(x).contiguous(memory_format=torch.channels_last))
-        q, k, v = (_pointwise(m, h).reshape(B, 1, H * W, C) for m in (self.q, self.k, self.v))
-        o = F.scaled_dot_product_attention(q, k, v)                     # scale C^-0.5 = the reference's int(c)**-0.5
+        q, k, v = (_pointwise(m, h).reshape(B, H * W, C) for m in (self.q, self.k, self.v))
+        # one head of width C = 512: outside the fused-attention kernels' head sizes (PyTorch falls back to an sm80
+        # memory-efficient kernel, 0.8 ms for its backward alone) — three plain tensor-core matmuls and a softmax, exactly
+        # the reference's formulation (model.py:176-188), scale int(c)**-0.5
+        w = torch.softmax(torch.bmm(q, k.transpose(1, 2)) * (float(C) ** -0.5), dim=-1)
+        o = torch.bmm(w, v)
         return x + _nchw(_pointwise(self.proj_out, o.reshape(B, H, W, C)))
 
 

@@ -326,6 +326,15 @@ int dm4d_groupnorm_nhwc_backward(const void* x, const float* chan_bias, const vo
                                  const float* beta, int32_t N, int32_t HW, int32_t C, int32_t G, float eps, int32_t silu,
                                  int32_t dtype, const float* stats, float* scratch, void* dx, void* stream);
 
+/* Epilogues the library convolutions / matmuls of the Zero123 networks do not fuse (channels-last, DM4D_F16 / DM4D_F32):
+ *   dm4d_bias_residual_add_nhwc: out[m,c] = h[m,c] + bias[c] (+ residual[m,c]) — the convolution bias folded into the
+ *     ResBlock's residual add (openaimodel.py:289, model.py:138); h, residual (or NULL), out: [M, C], bias [C] fp32, C % 4 == 0;
+ *   dm4d_geglu: out[m,d] = proj[m,d] * gelu(proj[m,D+d]) with the exact GELU — the gated feed-forward of the transformer
+ *     blocks (modules/attention.py:37-65); proj [M, 2D], out [M, D], D % 4 == 0. */
+int dm4d_bias_residual_add_nhwc(const void* h, const void* residual, const float* bias, int64_t M, int32_t C,
+                                int32_t dtype, void* out, void* stream);
+int dm4d_geglu(const void* proj, int64_t M, int32_t D, int32_t dtype, void* out, void* stream);
+
 /* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel launch).
  * Kernel ids: see DM4D_K_* below.  dm4d_profile_collect synchronises the recorded events, ADDS the
  * elapsed milliseconds / launch counts since the last collect into ms[DM4D_K_COUNT] /

@@ -103,3 +103,36 @@ def test_zero123_networks_on_the_fused_kernels_reproduce_the_reference():
     ic = torch.from_numpy(g["enc_x"]).clone().requires_grad_(True)
     (gc,) = torch.autograd.grad(enc_cpu(ic), ic, gl.cpu())
     assert Hh.rel_linf(gi.cpu().numpy(), gc.numpy()) <= 2e-4
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_bias_residual_add_matches_torch(dtype, tol, with_res):
+    from dreammesh4d_b200.nhwc import bias_residual_add
+    g = torch.Generator().manual_seed(11)
+    shape = (3, 132, 17, 9)
+    h = torch.randn(shape, generator=g).to(DEV, dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    res = torch.randn(shape, generator=g).to(DEV, dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True) if with_res else None
+    bias = torch.randn(shape[1], generator=g).to(DEV, dtype)
+    out = bias_residual_add(h, bias, res)
+    ref = h.float() + bias.float()[None, :, None, None] + (res.float() if with_res else 0.0)
+    assert out.dtype == dtype and Hh.rel_linf(out.detach().float().cpu(), ref.detach().cpu()) <= tol
+    gy = torch.randn(shape, generator=g).to(DEV, dtype)
+    grads = torch.autograd.grad(out, [h] + ([res] if with_res else []), gy)
+    for gr in grads:
+        assert torch.equal(gr, gy)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.float16, 2e-3)])
+def test_geglu_matches_torch(dtype, tol):
+    from dreammesh4d_b200.nhwc import geglu
+    g = torch.Generator().manual_seed(12)
+    proj = (2.0 * torch.randn(2, 37, 2 * 320, generator=g)).to(DEV, dtype).requires_grad_(True)
+    out = geglu(proj)
+    a, gate = proj.float().chunk(2, dim=-1)
+    ref = a * F.gelu(gate)
+    assert out.shape == (2, 37, 320) and Hh.rel_linf(out.detach().float().cpu(), ref.detach().cpu()) <= tol
+    gy = torch.randn(out.shape, generator=g).to(DEV, dtype)
+    (gp,) = torch.autograd.grad(out, proj, gy)
+    (gr,) = torch.autograd.grad(ref, proj, gy.float())
+    assert Hh.rel_linf(gp.float().cpu(), gr.float().cpu()) <= 5 * tol

@@ -79,22 +79,17 @@ def test_encoder_and_posterior_reproduce_reference(gold):
 
 
 def test_flop_counters_match_a_hook_count():
-    """unet_flops / encoder_flops (used for the tensor-pipe roofline in bench.py) against FLOPs counted by hooks on
-    the executed Linear / Conv2d modules plus the attention products."""
+    """unet_flops / encoder_flops (used for the tensor-pipe roofline in bench.py) against torch's own operator-level FLOP
+    counter (convolutions, matmuls, attention products of the modules as executed)."""
+    from torch.utils.flop_counter import FlopCounterMode
     unet = Z.Zero123UNet(SMALL_UNET).eval()
     n, h, w = 2, 8, 8
-    total = [0.0]
-
-    def hook(m, inp, out):
-        if isinstance(m, torch.nn.Conv2d):
-            total[0] += 2.0 * out.numel() * m.in_channels * m.kernel_size[0] * m.kernel_size[1]
-        elif isinstance(m, torch.nn.Linear):
-            total[0] += 2.0 * out.numel() * m.in_features
-    hs = [m.register_forward_hook(hook) for m in unet.modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))]
-    with torch.no_grad():
+    with FlopCounterMode(display=False) as fc, torch.no_grad():
         unet(torch.zeros(n, 8, h, w), torch.zeros(n, dtype=torch.long), torch.zeros(n, 1, 24))
-    for x in hs:
-        x.remove()
-    # 1x1 projections run as F.linear on the conv weights (no module call) and the attention products have no module
-    est = Z.unet_flops(SMALL_UNET, n, h, w)
-    assert est >= total[0] and est <= 1.35 * total[0]
+    est, counted = Z.unet_flops(SMALL_UNET, n, h, w), float(fc.get_total_flops())
+    assert 0.94 * est <= counted <= 1.06 * est, (est, counted)
+    enc = Z.Zero123Encoder(SMALL_ENC).eval()
+    with FlopCounterMode(display=False) as fc, torch.no_grad():
+        enc(torch.zeros(n, 3, 32, 32))
+    est, counted = Z.encoder_flops(SMALL_ENC, n, 32, 32), float(fc.get_total_flops())
+    assert 0.94 * est <= counted <= 1.06 * est, (est, counted)
