@@ -8,10 +8,15 @@
 //   y[n,p,c] = act( ((x[n,p,c] + e[n,c]) - mean[n,g]) * rstd[n,g] * gamma[c] + beta[c] ),   g = c / (C / G)
 //
 // Layout: x, y are [N, HW, C] (the memory of a torch channels_last [N,C,H,W] tensor), fp16 or fp32; statistics in fp32.
-// Two launches each way: (1) per-(sample, pixel-slab) partial sums -> [N,G,2] with one atomic per (block, group);
-// (2) element-wise apply with 8- / 16-byte vector accesses.  HBM-bound: forward reads x twice and writes y once.
+// ONE persistent launch each way.  Work items = (sample, pixel slab) x {statistics, apply}, handed out in order by an
+// atomic counter: the statistics items of sample n run a bounded distance (~24 MB of activations) ahead of its apply
+// items, so the apply pass finds the sample in the 126 MB L2 instead of re-reading HBM, and an apply item only waits
+// (on a per-sample arrival counter) for items that were fetched before it — deadlock-free without co-residency.
+// The encoder's 134 MB activations cost 3 HBM passes instead of 3 + 1 (forward) and 3 instead of 5 (backward); the
+// UNet's small ones one launch instead of three.
 // Backward (weights are frozen in the SDS step: no dgamma / dbeta) needs the two group sums of dz*gamma and dz*gamma*xhat.
 #include <algorithm>
+#include <cmath>
 #include <cuda_fp16.h>
 #include "raster_internal.cuh"
 
@@ -58,51 +63,187 @@ __device__ __forceinline__ float silu_grad(float z) {
     return s * (1.0f + z * (1.0f - s));
 }
 
-// Statistics: block = (C/VEC) x k threads; thread (cv, r) owns channels [cv*4, cv*4+4) and walks the pixels r, r+k, ...
-// of its slab.  Per-channel partial sums live in registers; at the end every thread folds its 4 channels into the
-// block's group bins in shared memory, and the block issues one global atomic per (group, moment).
+// Thread layout of a block: (C/VEC) x k threads; thread (cv, r) owns channels [cv*4, cv*4+4) and walks the pixels
+// r, r+k, ... of a slab (coalesced 8- / 16-byte accesses along the channel axis).  Statistics: per-channel partial sums
+// in registers, folded into the block's group bins in shared memory, one global atomic per (block, group, moment).
+// Backward: dx = rstd * (dz*gamma - mean_g(dz*gamma) - xhat * mean_g(dz*gamma*xhat)),  dz = dy * act'(z)
+// (d chan_bias is not produced: the time embedding carries no gradient in the SDS step).
+
+// ---- single-launch persistent GroupNorm ------------------------------------------------------------------------------
+struct FusedArgs {
+    NormArgs a;
+    int slabs;            // pixel slabs per sample
+    int ahead;            // statistics run this many samples ahead of the apply pass
+    float* sums;          // [N,G,2] zeroed: forward (sum, sum sq) / backward (sum dz*gamma, sum dz*gamma*xhat)
+    int* counters;        // [1 + N] zeroed: work counter, per-sample arrivals of statistics items
+};
+
+// group g of the item order  S(0..D-1), A(0), S(D), A(1), S(D+1), ..., A(N-D..N-1)
+__device__ __forceinline__ void decode_group(int g, int N, int D, bool& apply, int& n) {
+    if (g < D) { apply = false; n = g; }
+    else if (g < 2 * N - D) { const int r = g - D; apply = (r & 1) == 0; n = apply ? r / 2 : r / 2 + D; }
+    else { apply = true; n = g - N; }
+}
+
 template <typename T, bool BWD>
-__global__ void gn_stats_kernel(NormArgs a, const T* __restrict__ x, const float* __restrict__ chan_bias,
+__global__ void gn_fused_kernel(FusedArgs f, const T* __restrict__ x, const float* __restrict__ chan_bias,
                                 const T* __restrict__ dy, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ stats, float* __restrict__ sums) {
+                                float* __restrict__ stats /* fwd: out, bwd: in */, T* __restrict__ out) {
     __shared__ float bins[2 * MAX_GROUPS];
-    const int n = blockIdx.y;
+    __shared__ int s_item;
+    const NormArgs& a = f.a;
     const int cv = threadIdx.x % a.cvec, r = threadIdx.x / a.cvec, k = blockDim.x / a.cvec;
-    for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) bins[i] = 0.f;
-    __syncthreads();
-    const int p0 = blockIdx.x * a.rows_per_block, p1 = min(a.HW, p0 + a.rows_per_block);
     const int c0 = cv * VEC;
-    float s0[VEC], s1[VEC], e[VEC], gam[VEC], bet[VEC], mu[VEC], rs[VEC];
+    const int total = 2 * a.N * f.slabs;
+    const float count = (float)a.HW * (float)a.cpg, inv_count = 1.0f / count;
+    float gam[VEC], bet[VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        s0[j] = s1[j] = 0.f;
-        e[j] = chan_bias ? chan_bias[(size_t)n * a.C + c0 + j] : 0.f;
-        if (BWD) {
-            const int g = (c0 + j) / a.cpg;
-            gam[j] = gamma[c0 + j]; bet[j] = beta[c0 + j];
-            mu[j] = stats[((size_t)n * a.G + g) * 2]; rs[j] = stats[((size_t)n * a.G + g) * 2 + 1];
-        }
-    }
-    if (r < k && cv < a.cvec) {
-        for (int p = p0 + r; p < p1; p += k) {
-            const size_t off = ((size_t)n * a.HW + p) * a.C + c0;
-            float v[VEC];
-            Vec4<T>::load(x + off, v);
-            if (!BWD) {
+    for (int j = 0; j < VEC; ++j) { gam[j] = gamma[c0 + j]; bet[j] = beta[c0 + j]; }
+    // first item = blockIdx.x (the grid never exceeds the resident capacity, so statically assigned items cannot be
+    // stuck behind spinning CTAs), later ones from the counter: one same-address atomic per EXTRA item only
+    for (int item = blockIdx.x; item < total;) {
+        bool apply; int n;
+        decode_group(item / f.slabs, a.N, f.ahead, apply, n);
+        const int slab = item % f.slabs;
+        const int p0 = slab * a.rows_per_block, p1 = min(a.HW, p0 + a.rows_per_block);
+        float e[VEC], mu[VEC], rs[VEC];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) { const float t = v[j] + e[j]; s0[j] += t; s1[j] += t * t; }
-            } else {
-                float d[VEC];
-                Vec4<T>::load(dy + off, d);
+        for (int j = 0; j < VEC; ++j) e[j] = chan_bias ? chan_bias[(size_t)n * a.C + c0 + j] : 0.f;
+        if (apply || BWD) {
+            if (apply) {                               // all statistics items of sample n have arrived?
+                if (threadIdx.x == 0) {
+                    while (atomicAdd(&f.counters[1 + n], 0) < f.slabs) __nanosleep(64);
+                    __threadfence();
+                }
+                __syncthreads();
+            }
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    const float xh = (v[j] + e[j] - mu[j]) * rs[j];
-                    float dz = d[j];
-                    if (a.silu) dz *= silu_grad(xh * gam[j] + bet[j]);
-                    const float t = dz * gam[j];
-                    s0[j] += t; s1[j] += t * xh;
+            for (int j = 0; j < VEC; ++j) {
+                const size_t sg = ((size_t)n * a.G + (c0 + j) / a.cpg) * 2;
+                if (BWD) { mu[j] = stats[sg]; rs[j] = stats[sg + 1]; }
+                else {
+                    const float mean = __ldcg(&f.sums[sg]) * inv_count;
+                    mu[j] = mean;
+                    rs[j] = rsqrtf(fmaxf(__ldcg(&f.sums[sg + 1]) * inv_count - mean * mean, 0.f) + a.eps);
                 }
             }
+        }
+        if (!apply) {
+            for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) bins[i] = 0.f;
+            __syncthreads();
+            float s0[VEC], s1[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) s0[j] = s1[j] = 0.f;
+            for (int p = p0 + r; p < p1; p += k) {
+                const size_t off = ((size_t)n * a.HW + p) * a.C + c0;
+                float v[VEC];
+                Vec4<T>::load(x + off, v);
+                if (!BWD) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) { const float t = v[j] + e[j]; s0[j] += t; s1[j] += t * t; }
+                } else {
+                    float d[VEC];
+                    Vec4<T>::load(dy + off, d);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        const float xh = (v[j] + e[j] - mu[j]) * rs[j];
+                        float dz = d[j];
+                        if (a.silu) dz *= silu_grad(xh * gam[j] + bet[j]);
+                        const float t = dz * gam[j];
+                        s0[j] += t; s1[j] += t * xh;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const int g = (c0 + j) / a.cpg;
+                atomicAdd(&bins[2 * g], s0[j]);
+                atomicAdd(&bins[2 * g + 1], s1[j]);
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) atomicAdd(&f.sums[(size_t)n * 2 * a.G + i], bins[i]);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(&f.counters[1 + n], 1);
+        } else {
+            float b0[VEC], b1[VEC];
+            if (BWD) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const size_t sg = ((size_t)n * a.G + (c0 + j) / a.cpg) * 2;
+                    b0[j] = __ldcg(&f.sums[sg]) * inv_count; b1[j] = __ldcg(&f.sums[sg + 1]) * inv_count;
+                }
+            } else if (slab == 0 && r == 0) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    if ((c0 + j) % a.cpg == 0) {
+                        const size_t sg = ((size_t)n * a.G + (c0 + j) / a.cpg) * 2;
+                        stats[sg] = mu[j]; stats[sg + 1] = rs[j];
+                    }
+                }
+            }
+            for (int p = p0 + r; p < p1; p += k) {
+                const size_t off = ((size_t)n * a.HW + p) * a.C + c0;
+                float v[VEC], o[VEC];
+                Vec4<T>::load(x + off, v);
+                if (!BWD) {
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        const float z = (v[j] + e[j] - mu[j]) * rs[j] * gam[j] + bet[j];
+                        o[j] = a.silu ? silu_f(z) : z;
+                    }
+                } else {
+                    float d[VEC];
+                    Vec4<T>::load(dy + off, d);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        const float xh = (v[j] + e[j] - mu[j]) * rs[j];
+                        float dz = d[j];
+                        if (a.silu) dz *= silu_grad(xh * gam[j] + bet[j]);
+                        o[j] = rs[j] * (dz * gam[j] - b0[j] - xh * b1[j]);
+                    }
+                }
+                Vec4<T>::store(out + off, o);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = (int)gridDim.x + atomicAdd(&f.counters[0], 1);
+        __syncthreads();
+        item = s_item;
+    }
+}
+
+// Forward of SMALL activations (the UNet's: at most a few MB, one CTA per (sample, slab) with every CTA resident at once):
+// the slab stays in registers between the statistics and the apply phase — x is read once, and the whole norm is one
+// launch whose critical path is load -> group atomics -> per-sample arrival counter -> store.  fp16 only.
+constexpr int RES_IT = 12;                 // pixels per thread kept in registers (packed fp16: 2 registers each)
+
+__global__ void __launch_bounds__(1024, 1) gn_resident_kernel(FusedArgs f, const __half* __restrict__ x, const float* __restrict__ chan_bias,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ stats, __half* __restrict__ out) {
+    __shared__ float bins[2 * MAX_GROUPS];
+    const NormArgs& a = f.a;
+    const int n = blockIdx.x / f.slabs, slab = blockIdx.x - n * f.slabs;
+    const int cv = threadIdx.x % a.cvec, r = threadIdx.x / a.cvec, k = blockDim.x / a.cvec;
+    const int c0 = cv * VEC;
+    const int p0 = slab * a.rows_per_block, p1 = min(a.HW, p0 + a.rows_per_block);
+    const float inv_count = 1.0f / ((float)a.HW * (float)a.cpg);
+    for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) bins[i] = 0.f;
+    __syncthreads();
+    float e[VEC], s0[VEC], s1[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { e[j] = chan_bias ? chan_bias[(size_t)n * a.C + c0 + j] : 0.f; s0[j] = s1[j] = 0.f; }
+    uint2 raw[RES_IT];
+#pragma unroll
+    for (int it = 0; it < RES_IT; ++it) {
+        const int p = p0 + r + it * k;
+        if (p < p1) {
+            raw[it] = *reinterpret_cast<const uint2*>(x + ((size_t)n * a.HW + p) * a.C + c0);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw[it].x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw[it].y));
+            const float v[VEC] = {lo.x + e[0], lo.y + e[1], hi.x + e[2], hi.y + e[3]};
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) { s0[j] += v[j]; s1[j] += v[j] * v[j]; }
         }
     }
 #pragma unroll
@@ -112,72 +253,38 @@ __global__ void gn_stats_kernel(NormArgs a, const T* __restrict__ x, const float
         atomicAdd(&bins[2 * g + 1], s1[j]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) atomicAdd(&sums[(size_t)n * 2 * a.G + i], bins[i]);
-}
-
-// sums [N,G,2] (sum, sum of squares) -> stats [N,G,2] (mean, rstd)
-__global__ void gn_finalize_kernel(int total, float count, float eps, const float* __restrict__ sums, float* __restrict__ stats) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const float mean = sums[2 * i] / count;
-    const float var = fmaxf(sums[2 * i + 1] / count - mean * mean, 0.f);
-    stats[2 * i] = mean;
-    stats[2 * i + 1] = rsqrtf(var + eps);
-}
-
-template <typename T>
-__global__ void gn_apply_kernel(NormArgs a, const T* __restrict__ x, const float* __restrict__ chan_bias,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ stats, T* __restrict__ y) {
-    const size_t total = (size_t)a.N * a.HW * a.cvec;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % a.cvec);
-        const size_t np = i / a.cvec;
-        const int n = (int)(np / a.HW);
-        const int c0 = cv * VEC;
-        float v[VEC], o[VEC];
-        Vec4<T>::load(x + np * a.C + c0, v);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const int c = c0 + j, g = c / a.cpg;
-            const float mean = stats[((size_t)n * a.G + g) * 2], rstd = stats[((size_t)n * a.G + g) * 2 + 1];
-            const float e = chan_bias ? chan_bias[(size_t)n * a.C + c] : 0.f;
-            const float z = (v[j] + e - mean) * rstd * gamma[c] + beta[c];
-            o[j] = a.silu ? silu_f(z) : z;
-        }
-        Vec4<T>::store(y + np * a.C + c0, o);
+    for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) atomicAdd(&f.sums[(size_t)n * 2 * a.G + i], bins[i]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&f.counters[1 + n], 1);
+        while (atomicAdd(&f.counters[1 + n], 0) < f.slabs) __nanosleep(32);
+        __threadfence();
     }
-}
-
-// dx = rstd * (dz*gamma - mean_g(dz*gamma) - xhat * mean_g(dz*gamma*xhat)),  dz = dy * act'(z)
-// (d chan_bias = sum over pixels of dx is not produced: the time embedding carries no gradient in the SDS step)
-template <typename T>
-__global__ void gn_backward_apply_kernel(NormArgs a, const T* __restrict__ x, const float* __restrict__ chan_bias,
-                                         const T* __restrict__ dy, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, const float* __restrict__ stats,
-                                         const float* __restrict__ bsums, T* __restrict__ dx) {
-    const size_t total = (size_t)a.N * a.HW * a.cvec;
-    const float inv_count = 1.0f / ((float)a.HW * (float)a.cpg);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % a.cvec);
-        const size_t np = i / a.cvec;
-        const int n = (int)(np / a.HW);
-        const int c0 = cv * VEC;
-        float v[VEC], d[VEC], o[VEC];
-        Vec4<T>::load(x + np * a.C + c0, v);
-        Vec4<T>::load(dy + np * a.C + c0, d);
+    __syncthreads();
+    float sc[VEC], sh[VEC];                 // y = act(v * sc + sh)
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const int c = c0 + j, g = c / a.cpg;
-            const size_t sg = ((size_t)n * a.G + g) * 2;
-            const float mean = stats[sg], rstd = stats[sg + 1];
-            const float e = chan_bias ? chan_bias[(size_t)n * a.C + c] : 0.f;
-            const float xh = (v[j] + e - mean) * rstd;
-            float dz = d[j];
-            if (a.silu) dz *= silu_grad(xh * gamma[c] + beta[c]);
-            o[j] = rstd * (dz * gamma[c] - bsums[sg] * inv_count - xh * bsums[sg + 1] * inv_count);
+    for (int j = 0; j < VEC; ++j) {
+        const size_t sg = ((size_t)n * a.G + (c0 + j) / a.cpg) * 2;
+        const float mean = __ldcg(&f.sums[sg]) * inv_count;
+        const float rstd = rsqrtf(fmaxf(__ldcg(&f.sums[sg + 1]) * inv_count - mean * mean, 0.f) + a.eps);
+        if (slab == 0 && r == 0 && (c0 + j) % a.cpg == 0) { stats[sg] = mean; stats[sg + 1] = rstd; }
+        sc[j] = rstd * gamma[c0 + j];
+        sh[j] = (e[j] - mean) * sc[j] + beta[c0 + j];
+    }
+#pragma unroll
+    for (int it = 0; it < RES_IT; ++it) {
+        const int p = p0 + r + it * k;
+        if (p < p1) {
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw[it].x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw[it].y));
+            float o[VEC] = {lo.x * sc[0] + sh[0], lo.y * sc[1] + sh[1], hi.x * sc[2] + sh[2], hi.y * sc[3] + sh[3]};
+            if (a.silu) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) o[j] = silu_f(o[j]);
+            }
+            Vec4<__half>::store(out + ((size_t)n * a.HW + p) * a.C + c0, o);
         }
-        Vec4<T>::store(dx + np * a.C + c0, o);
     }
 }
 
@@ -189,43 +296,73 @@ int make_args(int N, int HW, int C, int G, float eps, int silu, NormArgs* a, int
     a->N = N; a->HW = HW; a->C = C; a->G = G; a->cpg = C / G; a->cvec = C / VEC; a->eps = eps; a->silu = silu;
     const int k = max(1, min(256 / a->cvec, HW));
     *threads = a->cvec * k;
-    // enough blocks per sample to fill the machine (148 SMs x a few CTAs), at least 8 pixels per thread row
+    // enough work items per sample to fill the machine (148 SMs x a few CTAs), at least 8 pixels per thread row
+    // (coarser items were measured slower even for the UNet's 10 MB activations: fewer CTAs in flight per pass)
     int slabs = max(1, min((HW + 8 * k - 1) / (8 * k), max(1, (148 * 8 + N - 1) / N)));
     a->rows_per_block = (HW + slabs - 1) / slabs;
     *grid = dim3((unsigned)((HW + a->rows_per_block - 1) / a->rows_per_block), (unsigned)N);
     return DM4D_OK;
 }
 
-unsigned apply_blocks(const NormArgs& a) {
-    const size_t total = (size_t)a.N * a.HW * a.cvec;
-    return (unsigned)min((size_t)148 * 16, (total + 255) / 256);
+template <typename T, bool BWD>
+int launch_fused(const NormArgs& a, int threads, dim3 grid, const void* x, const float* cb, const void* dy, const float* gamma,
+                 const float* beta, float* stats, float* scratch, void* out, cudaStream_t s) {
+    FusedArgs f;
+    f.a = a;
+    f.slabs = (int)grid.x;
+    // statistics lead the apply pass by ~24 MB of activations (x, and dy in the backward): well inside the L2
+    const double sample_bytes = (double)a.HW * a.C * sizeof(T) * (BWD ? 2 : 1);
+    f.ahead = (int)std::max(1.0, std::min((double)a.N, std::ceil(24e6 / sample_bytes)));
+    f.sums = scratch;
+    f.counters = reinterpret_cast<int*>(scratch + (size_t)a.N * a.G * 2);
+    DM4D_CUDA_CHECK(cudaMemsetAsync(scratch, 0, ((size_t)a.N * a.G * 2 + a.N + 1) * sizeof(float), s));
+    const int total = 2 * a.N * f.slabs;
+    int per_sm = 0;
+    DM4D_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel<T, BWD>, threads, 0));
+    const unsigned blocks = (unsigned)std::min(total, 148 * std::max(1, per_sm));
+    {
+        KernelTimer kt(BWD ? DM4D_K_GROUPNORM_BWD : DM4D_K_GROUPNORM_FWD, s);
+        gn_fused_kernel<T, BWD><<<blocks, threads, 0, s>>>(f, (const T*)x, cb, (const T*)dy, gamma, beta, stats, (T*)out);
+    }
+    DM4D_CUDA_CHECK(cudaGetLastError());
+    return DM4D_OK;
 }
 
 template <typename T>
 int forward_t(const NormArgs& a, int threads, dim3 grid, const void* x, const float* cb, const float* gamma, const float* beta,
               float* stats, float* scratch, void* y, cudaStream_t s) {
-    DM4D_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)a.N * a.G * 2 * sizeof(float), s));
-    {
-        KernelTimer kt(DM4D_K_GROUPNORM_FWD, s);
-        gn_stats_kernel<T, false><<<grid, threads, 0, s>>>(a, (const T*)x, cb, nullptr, nullptr, nullptr, nullptr, scratch);
-        gn_finalize_kernel<<<(a.N * a.G + 127) / 128, 128, 0, s>>>(a.N * a.G, (float)a.HW * (float)a.cpg, a.eps, scratch, stats);
-        gn_apply_kernel<T><<<apply_blocks(a), 256, 0, s>>>(a, (const T*)x, cb, gamma, beta, stats, (T*)y);
+    if constexpr (sizeof(T) == 2) {
+        // resident single-pass variant when one CTA per (sample, slab) fits on the machine at once with <= RES_IT pixels per thread
+        static int per_sm_cache[33] = {0};
+        int& per_sm = per_sm_cache[threads / 32];
+        if (per_sm == 0) DM4D_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_resident_kernel, threads, 0));
+        const int k = threads / a.cvec;
+        const int slabs = std::min((a.HW + k - 1) / k, std::max(1, 148 * per_sm / a.N));
+        const int rows = (a.HW + slabs - 1) / slabs;
+        if (a.N * slabs <= 148 * per_sm && (rows + k - 1) / k <= RES_IT) {
+            FusedArgs f;
+            f.a = a;
+            f.a.rows_per_block = rows;
+            f.slabs = (a.HW + rows - 1) / rows;
+            f.ahead = a.N;
+            f.sums = scratch;
+            f.counters = reinterpret_cast<int*>(scratch + (size_t)a.N * a.G * 2);
+            DM4D_CUDA_CHECK(cudaMemsetAsync(scratch, 0, ((size_t)a.N * a.G * 2 + a.N + 1) * sizeof(float), s));
+            {
+                KernelTimer kt(DM4D_K_GROUPNORM_FWD, s);
+                gn_resident_kernel<<<(unsigned)(a.N * f.slabs), threads, 0, s>>>(f, (const __half*)x, cb, gamma, beta, stats, (__half*)y);
+            }
+            DM4D_CUDA_CHECK(cudaGetLastError());
+            return DM4D_OK;
+        }
     }
-    DM4D_CUDA_CHECK(cudaGetLastError());
-    return DM4D_OK;
+    return launch_fused<T, false>(a, threads, grid, x, cb, nullptr, gamma, beta, stats, scratch, y, s);
 }
 
 template <typename T>
 int backward_t(const NormArgs& a, int threads, dim3 grid, const void* x, const float* cb, const void* dy, const float* gamma,
                const float* beta, const float* stats, float* scratch, void* dx, cudaStream_t s) {
-    DM4D_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)a.N * a.G * 2 * sizeof(float), s));
-    {
-        KernelTimer kt(DM4D_K_GROUPNORM_BWD, s);
-        gn_stats_kernel<T, true><<<grid, threads, 0, s>>>(a, (const T*)x, cb, (const T*)dy, gamma, beta, stats, scratch);
-        gn_backward_apply_kernel<T><<<apply_blocks(a), 256, 0, s>>>(a, (const T*)x, cb, (const T*)dy, gamma, beta, stats, scratch, (T*)dx);
-    }
-    DM4D_CUDA_CHECK(cudaGetLastError());
-    return DM4D_OK;
+    return launch_fused<T, true>(a, threads, grid, x, cb, dy, gamma, beta, const_cast<float*>(stats), scratch, dx, s);
 }
 
 // ---- convolution epilogues the library calls do not fuse ------------------------------------------------------------

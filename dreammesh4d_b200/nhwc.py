@@ -30,7 +30,7 @@ class _GroupNormNHWC(torch.autograd.Function):
         cb = None if chan_bias is None else chan_bias.detach().float().contiguous()
         f32 = dict(dtype=torch.float32, device=x.device)
         stats = torch.empty(N, groups, 2, **f32)
-        scratch = torch.empty(N, groups, 2, **f32)
+        scratch = torch.empty(N * groups * 2 + N + 1, **f32)
         y = torch.empty_like(x, memory_format=torch.channels_last)
         check(_lib.lib().dm4d_groupnorm_nhwc_forward(ptr(x), ptr(cb), ptr(gamma), ptr(beta), N, H * W, C, groups, float(eps),
                                                      int(silu), _DTYPES[x.dtype], ptr(stats), ptr(scratch), ptr(y),
@@ -48,7 +48,7 @@ class _GroupNormNHWC(torch.autograd.Function):
         N, C, H, W = x.shape
         dy = dy.to(x.dtype).contiguous(memory_format=torch.channels_last)
         dx = torch.empty_like(x, memory_format=torch.channels_last)
-        scratch = torch.empty(N, groups, 2, dtype=torch.float32, device=x.device)
+        scratch = torch.empty(N * groups * 2 + N + 1, dtype=torch.float32, device=x.device)
         check(_lib.lib().dm4d_groupnorm_nhwc_backward(ptr(x), ptr(cb), ptr(dy), ptr(gamma), ptr(beta), N, H * W, C, groups, eps, silu,
                                                       _DTYPES[x.dtype], ptr(stats), ptr(scratch), ptr(dx),
                                                       torch.cuda.current_stream().cuda_stream), "dm4d_groupnorm_nhwc_backward")

@@ -13,7 +13,6 @@ import bench  # noqa: E402
 
 def main():
     dev = torch.device("cuda", 0)
-    scene, graph, node = bench.build_scene(False)
     holder = {}
     orig = torch.cuda.synchronize
 
@@ -35,7 +34,7 @@ def main():
         return real_call(self, batches, step)
 
     TS.DynamicStageStep.__call__ = wrapped
-    res = bench.train_step_ms(scene, graph, bench.cams_c2w_fovy(0), dev, None, steps=5)
+    res = bench.train_step_ms(dev, None, 5, bench.N_FACES, bench.VIEWS, 32, "C3")
     print({k: v for k, v in res.items() if k != "what"})
     prof = holder["prof"]
     rows = [(e.key, e.device_time_total / 3e3, e.count // 3) for e in prof.key_averages() if e.device_time_total > 0]
