@@ -97,6 +97,8 @@ SIGNATURES = {
     "dm4d_last_error": (c_char_p, []),
     "dm4d_bias_residual_add_nhwc": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "dm4d_geglu": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "dm4d_add_layernorm": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, ctypes.c_int64, c_int32, ctypes.c_float,
+                                          c_int32, c_void_p, c_void_p, c_void_p]),
     "dm4d_version": (ctypes.c_int, []),
 }
 

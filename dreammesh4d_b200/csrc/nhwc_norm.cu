@@ -34,6 +34,7 @@ template <> struct Vec4<float> {
     static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
+    static __device__ __forceinline__ void round(float (&)[4]) {}
 };
 template <> struct Vec4<__half> {
     static __device__ __forceinline__ void load(const __half* p, float (&v)[4]) {
@@ -47,6 +48,10 @@ template <> struct Vec4<__half> {
         *reinterpret_cast<__half2*>(&t.x) = __floats2half2_rn(v[0], v[1]);
         *reinterpret_cast<__half2*>(&t.y) = __floats2half2_rn(v[2], v[3]);
         *reinterpret_cast<uint2*>(p) = t;
+    }
+    static __device__ __forceinline__ void round(float (&v)[4]) {      // what a store + load in this dtype would give
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __half2float(__float2half_rn(v[j]));
     }
 };
 
@@ -405,6 +410,78 @@ __global__ void __launch_bounds__(256) geglu_kernel(long long nvec, int dvec, co
     }
 }
 
+// Residual add + LayerNorm of the transformer blocks (attention.py:199-246: x = x + attn(norm(x)) three times per block):
+// x_out[m,:] = x[m,:] + delta[m or m / bcast_rows,:],  y[m,:] = LayerNorm(x_out[m,:]) * gamma + beta.  One warp per row,
+// the row stays in registers (C <= 1536); eager PyTorch runs the add and a slower LayerNorm kernel as two passes.
+constexpr int LN_MAXV = 12;                // 4-channel vectors per lane
+template <typename T>
+__global__ void __launch_bounds__(256) add_layernorm_kernel(long long M, int C, const T* __restrict__ x, const T* __restrict__ delta,
+                                                            int bcast_rows, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, T* __restrict__ x_out,
+                                                            T* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nvec = C / VEC;
+    const T* xr = x + row * C;
+    const T* dr = delta ? delta + (bcast_rows > 0 ? row / bcast_rows : row) * C : nullptr;
+    float v[LN_MAXV][VEC];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) {
+            Vec4<T>::load(xr + vi * VEC, v[i]);
+            if (dr) {
+                float d[VEC];
+                Vec4<T>::load(dr + vi * VEC, d);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) v[i][j] += d[j];
+                if (x_out) {
+                    // the residual stream continues in the activation dtype: normalise what was stored
+                    Vec4<T>::store(x_out + row * C + vi * VEC, v[i]);
+                    Vec4<T>::round(v[i]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) sum += v[i][j];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        if (lane + 32 * i < nvec) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) { const float t = v[i][j] - mean; sq += t * t; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) {
+            const float4 g = *reinterpret_cast<const float4*>(gamma + vi * VEC), b = *reinterpret_cast<const float4*>(beta + vi * VEC);
+            const float o[VEC] = {(v[i][0] - mean) * rstd * g.x + b.x, (v[i][1] - mean) * rstd * g.y + b.y,
+                                  (v[i][2] - mean) * rstd * g.z + b.z, (v[i][3] - mean) * rstd * g.w + b.w};
+            Vec4<T>::store(y + row * C + vi * VEC, o);
+        }
+    }
+}
+
+template <typename T>
+int launch_add_layernorm(long long M, int C, const void* x, const void* delta, int bcast_rows, const float* gamma, const float* beta,
+                         float eps, void* x_out, void* y, cudaStream_t s) {
+    const unsigned blocks = (unsigned)((M + 7) / 8);
+    add_layernorm_kernel<T><<<blocks, 256, 0, s>>>(M, C, (const T*)x, (const T*)delta, bcast_rows, gamma, beta, eps, (T*)x_out, (T*)y);
+    DM4D_CUDA_CHECK(cudaGetLastError());
+    return DM4D_OK;
+}
+
 template <typename T>
 int launch_bias_residual(long long M, int C, const void* h, const void* res, const float* bias, void* out, cudaStream_t s) {
     const long long nvec = M * (C / VEC);
@@ -430,6 +507,18 @@ extern "C" int dm4d_bias_residual_add_nhwc(const void* h, const void* residual, 
     if (dtype == DM4D_F16) return launch_bias_residual<__half>(M, C, h, residual, bias, out, (cudaStream_t)stream);
     if (dtype == DM4D_F32) return launch_bias_residual<float>(M, C, h, residual, bias, out, (cudaStream_t)stream);
     dm4d_set_error("dm4d_bias_residual_add_nhwc: dtype must be DM4D_F16 or DM4D_F32");
+    return DM4D_EINVAL;
+}
+
+extern "C" int dm4d_add_layernorm(const void* x, const void* delta, int32_t delta_bcast_rows, const float* gamma, const float* beta,
+                                  int64_t M, int32_t C, float eps, int32_t dtype, void* x_out, void* y, void* stream) {
+    if (!x || !gamma || !beta || !y || M <= 0 || C <= 0 || C % VEC || C > 32 * VEC * LN_MAXV || (delta && !x_out) || delta_bcast_rows < 0) {
+        dm4d_set_error("dm4d_add_layernorm: bad argument (C %% 4 == 0, C <= %d, x_out required with delta)", 32 * VEC * LN_MAXV);
+        return DM4D_EINVAL;
+    }
+    if (dtype == DM4D_F16) return launch_add_layernorm<__half>(M, C, x, delta, delta_bcast_rows, gamma, beta, eps, x_out, y, (cudaStream_t)stream);
+    if (dtype == DM4D_F32) return launch_add_layernorm<float>(M, C, x, delta, delta_bcast_rows, gamma, beta, eps, x_out, y, (cudaStream_t)stream);
+    dm4d_set_error("dm4d_add_layernorm: dtype must be DM4D_F16 or DM4D_F32");
     return DM4D_EINVAL;
 }
 

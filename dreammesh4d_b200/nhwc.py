@@ -148,3 +148,34 @@ def geglu(proj: torch.Tensor) -> torch.Tensor:
         return _GEGLU.apply(proj)
     a, gate = proj.chunk(2, dim=-1)
     return a * F.gelu(gate)
+
+
+def add_layernorm(x: torch.Tensor, delta: Optional[torch.Tensor], ln: nn.LayerNorm):
+    """``x_new = x + delta`` (``delta`` [B,N,C] or broadcast [B,1,C]; None: ``x_new = x``) and ``LayerNorm(x_new)`` in one
+    pass (``dm4d_add_layernorm``) when no gradient is recorded — the UNet of the SDS step — else with torch ops.
+    Returns ``(x_new, y)``."""
+    C = x.shape[-1]
+    fast = (x.is_cuda and x.dtype in _DTYPES and C % 4 == 0 and C <= 1536 and x.dim() == 3 and
+            not (torch.is_grad_enabled() and (x.requires_grad or (delta is not None and delta.requires_grad) or ln.weight.requires_grad)))
+    if not fast:
+        x_new = x if delta is None else x + delta
+        return x_new, F.layer_norm(x_new, (C,), ln.weight, ln.bias, ln.eps)
+    B, N, _ = x.shape
+    xc = x.contiguous()
+    bcast, d = 0, None
+    if delta is not None:
+        if delta.shape[1] == 1 or delta.stride(1) == 0:
+            d, bcast = delta[:, :1].to(x.dtype).contiguous(), N
+        else:
+            d = delta.to(x.dtype).contiguous()
+    cache = getattr(ln, "_dm4d_p32", None)
+    key = (ln.weight._version, ln.bias._version, ln.weight.data_ptr(), ln.weight.device)
+    if cache is None or cache[0] != key:
+        cache = (key, ln.weight.detach().float().contiguous(), ln.bias.detach().float().contiguous())
+        ln._dm4d_p32 = cache
+    x_new = torch.empty_like(xc) if d is not None else xc
+    y = torch.empty_like(xc)
+    check(_lib.lib().dm4d_add_layernorm(ptr(xc), ptr(d), bcast, ptr(cache[1]), ptr(cache[2]), B * N, C, float(ln.eps),
+                                        _DTYPES[x.dtype], ptr(x_new) if d is not None else None, ptr(y),
+                                        torch.cuda.current_stream().cuda_stream), "dm4d_add_layernorm")
+    return x_new, y

@@ -32,7 +32,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .nhwc import GroupNormAct, bias_residual_add, conv_nobias, geglu
+from .nhwc import GroupNormAct, add_layernorm, bias_residual_add, conv_nobias, geglu
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -182,9 +182,11 @@ class TransformerBlock(nn.Module):
         self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
 
     def forward(self, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
-        x = x + self.attn1(self.norm1(x))
-        x = x + self.attn2(self.norm2(x), context)
-        return x + self.ff(self.norm3(x))
+        # each residual add rides with the LayerNorm that follows it (one pass; plain torch ops when gradients are recorded)
+        x, h = add_layernorm(x, None, self.norm1)
+        x, h = add_layernorm(x, self.attn1(h), self.norm2)
+        x, h = add_layernorm(x, self.attn2(h, context), self.norm3)
+        return x + self.ff(h)
 
 
 class SpatialTransformer(nn.Module):

@@ -335,6 +335,13 @@ int dm4d_groupnorm_nhwc_backward(const void* x, const float* chan_bias, const vo
 int dm4d_bias_residual_add_nhwc(const void* h, const void* residual, const float* bias, int64_t M, int32_t C,
                                 int32_t dtype, void* out, void* stream);
 int dm4d_geglu(const void* proj, int64_t M, int32_t D, int32_t dtype, void* out, void* stream);
+/* Residual add + LayerNorm of the transformer blocks (modules/attention.py:199-246): x_out[m,:] = x[m,:] + delta[r,:] with
+ * r = m (delta_bcast_rows == 0) or m / delta_bcast_rows (one delta row shared by that many consecutive rows: the
+ * single-token cross-attention output); y[m,:] = LayerNorm(x_out[m,:]) * gamma + beta.  delta / x_out may be NULL (plain
+ * LayerNorm of x).  x, delta, x_out, y: [M, C] in `dtype`; gamma, beta [C] fp32; C % 4 == 0, C <= 1536.  Forward only
+ * (the UNet of the SDS step runs without gradient). */
+int dm4d_add_layernorm(const void* x, const void* delta, int32_t delta_bcast_rows, const float* gamma, const float* beta,
+                       int64_t M, int32_t C, float eps, int32_t dtype, void* x_out, void* y, void* stream);
 
 /* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel launch).
  * Kernel ids: see DM4D_K_* below.  dm4d_profile_collect synchronises the recorded events, ADDS the

@@ -136,3 +136,31 @@ def test_geglu_matches_torch(dtype, tol):
     (gp,) = torch.autograd.grad(out, proj, gy)
     (gr,) = torch.autograd.grad(ref, proj, gy.float())
     assert Hh.rel_linf(gp.float().cpu(), gr.float().cpu()) <= 5 * tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("mode", ["none", "full", "broadcast"])
+@pytest.mark.parametrize("C", [320, 1280, 36])
+def test_add_layernorm_matches_torch(dtype, tol, mode, C):
+    from dreammesh4d_b200.nhwc import add_layernorm
+    g = torch.Generator().manual_seed(C)
+    B, N = 3, 50
+    ln = torch.nn.LayerNorm(C).to(DEV, dtype)
+    with torch.no_grad():
+        ln.weight.copy_(1 + 0.3 * torch.randn(C, generator=g)); ln.bias.copy_(0.2 * torch.randn(C, generator=g))
+    x = (1.5 * torch.randn(B, N, C, generator=g)).to(DEV, dtype)
+    delta = None if mode == "none" else torch.randn(B, N if mode == "full" else 1, C, generator=g).to(DEV, dtype)
+    if mode == "broadcast":
+        delta = delta.expand(B, N, C)
+    with torch.no_grad():
+        x_new, y = add_layernorm(x, delta, ln)
+    with torch.no_grad():
+        x_ref = x if delta is None else x + delta
+        y_ref = F.layer_norm(x_ref.float(), (C,), ln.weight.float(), ln.bias.float(), ln.eps)
+    assert torch.equal(x_new, x_ref)
+    assert y.dtype == dtype and Hh.rel_linf(y.float().cpu(), y_ref.cpu()) <= tol
+    # with gradients recorded the torch path is taken and differentiable
+    xg = x.clone().requires_grad_(True)
+    _, y2 = add_layernorm(xg, delta, ln)
+    y2.float().sum().backward()
+    assert xg.grad is not None
