@@ -22,7 +22,9 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 
 _INCIDENCE: dict = {}
-USE_NODE_INCIDENCE = True     # False: the C ABI's list-free backward (per-CTA node tables, shared-memory atomics)
+USE_NODE_INCIDENCE = True     # node-centric backward over incidence lists (no atomics on the node tables, reproducible
+                              # summation order; 226 us at C5 x 8 timestamps); False: the C ABI's list-free backward
+                              # (warp-aggregated floating-point reductions, 428 us there)
 
 
 def node_incidence(nbr_idx: torch.Tensor, M: int):

@@ -145,9 +145,8 @@ def test_rest_frames_backward_static_stage():
 
 
 def test_node_incidence_lists_and_list_free_backward():
-    """dm4d_skin_node_incidence vs a numpy stable sort; the node-centric backward and the list-free backward (the C
-    ABI's path when the desc carries no lists) produce the same gradients; the node-centric one is bit-reproducible
-    when it runs unsplit (M * n_t >= 1184)."""
+    """dm4d_skin_node_incidence vs a numpy stable sort; the node-centric backward (incidence lists) and the list-free
+    warp-aggregated backward (the C ABI's path when the desc carries no lists) produce the same gradients."""
     scene = synthetic.make_sugar_scene(6_000, g=3)
     M, T = 160, 8
     graph = synthetic.make_deform_graph(scene.verts, M, 4)
