@@ -5,6 +5,8 @@ bit-exact integer state (radii, tile ranges, sorted instance ids, n_contrib).  P
 compositing decisions sit within the oracle's ambiguity margin of a hard threshold
 (alpha < 1/255, T < 1e-4, power > 0) are excluded and counted.
 """
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -251,3 +253,27 @@ def test_dropin_shs_path_equals_precomputed_colours():
         assert torch.equal(c1, c2) and torch.equal(r1, r2) and torch.equal(d1, d2) and torch.equal(a1, a2)
         c1.sum().backward()
         assert shs.grad is not None and float(shs.grad.abs().max()) > 0
+
+
+@pytest.mark.parametrize("P", [1023, 1024, 1025, 4096, 4097, 8192, 8193, 16384, 16385, 21000])
+def test_tile_sort_tier_boundaries(P):
+    """One 16x16 image = one tile holding every Gaussian: segment lengths on both sides of every tier of the per-tile
+    sort (128x8, 512x8, 1024x8, 1024x16 keys in shared memory, chunked merging through global memory above 16384).
+    Sorted instance ids and tile ranges bit-exact against the oracle; duplicated depths exercise the (depth, id) order."""
+    g = torch.Generator().manual_seed(P)
+    means = 0.15 * (torch.rand(P, 3, generator=g) - 0.5)
+    means[: P // 7, 2] = means[P // 7: 2 * (P // 7), 2][: P // 7]          # ties in view-space depth for an axis-aligned camera
+    scales = torch.exp(torch.rand(P, 3, generator=g) * (math.log(0.03) - math.log(0.005)) + math.log(0.005))
+    rots = torch.nn.functional.normalize(torch.randn(P, 4, generator=g), dim=-1)
+    opac = torch.rand(P, 1, generator=g) * 0.5 + 0.05
+    cols = torch.rand(P, 3, generator=g)
+    H = W = 16
+    V, PV, campos, tanx, tany = Hh.cameras(1, seed=3)
+    bg = torch.tensor([0.0, 0.0, 0.0])
+    o = run_oracle(P, H, W, means, scales, rots, opac, cols, V[0], PV[0], tanx[0], tany[0], bg)
+    vp = R.make_view_params(V.to(DEV), PV.to(DEV), campos.to(DEV), tanx, tany, bg[None].to(DEV))
+    states = []
+    d = lambda x: x.to(DEV)
+    color, radii, depth, alpha = R.rasterize_batch(d(means), d(opac), d(scales), d(rots), d(cols), vp, H, W, state_out=states)
+    assert int((radii[0] > 0).sum()) == P                                  # nothing culled: the tile's segment has P keys
+    check_view(o, color[0], radii[0], depth[0], alpha[0], states[0], 0, max_ambig=0.05)

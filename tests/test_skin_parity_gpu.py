@@ -181,3 +181,13 @@ def test_node_incidence_lists_and_list_free_backward():
         # dverts / dvert_rot come from the (atomic) Gaussian stage, so bit-equality is not expected across runs
         assert Hh.rel_linf(x.cpu().double(), y.cpu().double()) <= 1e-5
         assert Hh.rel_linf(x.cpu().double(), z.cpu().double()) <= 1e-4
+
+
+@pytest.mark.parametrize("n_faces,g,M,K,T", [(1002, 4, 7, 3, 3), (330, 1, 2, 1, 5), (2050, 6, 40, 8, 2)])
+def test_skin_ragged_sizes(n_faces, g, M, K, T):
+    """Face counts that are no multiple of the warp size (warps straddle two timestamps in the staged Gaussian kernels),
+    every Gaussians-per-face pattern, K = 1 and tiny graphs (node lists far longer than a CTA, split over CTAs)."""
+    scene = synthetic.make_sugar_scene(n_faces, g=g)
+    graph = synthetic.make_deform_graph(scene.verts, M, K)
+    node = synthetic.random_node_attrs(T, M, seed=n_faces)
+    run_both(scene, graph, node, "hybrid", seed=g)
