@@ -83,20 +83,21 @@ __device__ __forceinline__ unsigned int preprocess_one(const PreArgs& a, long lo
 // global atomic per touched tile; blocks that straddle two views or very large images count globally.
 __global__ void __launch_bounds__(DM4D_BLOCK) preprocess_kernel(PreArgs a) {
     __shared__ unsigned int hist[SMEM_TILES];
-    __shared__ ViewCache vc;
+    __shared__ ViewCache vcache;
+    ViewRows vc;
     const long long total = (long long)a.n_views * a.P;
     const long long first = (long long)blockIdx.x * blockDim.x;
     const long long last = min(first + blockDim.x, total) - 1;
     const long long idx = first + threadIdx.x;
     const int v_first = (int)(first / a.P);
     const bool use_smem = a.tiles <= SMEM_TILES && v_first == (int)(last / a.P);
-    vc.fill(a.view_params, v_first, a.n_views);
+    vc.fill(&vcache, a.view_params, v_first, a.n_views);
     if (use_smem)
         for (int i = threadIdx.x; i < a.tiles; i += blockDim.x) hist[i] = 0u;
     __syncthreads();
     int v = 0, g = 0;
     if (idx < total) split_index(first, threadIdx.x, a.P, v, g);
-    const unsigned int rect = idx < total ? preprocess_one(a, idx, v, g, vc.row(a.view_params, v)) : 0u;
+    const unsigned int rect = idx < total ? preprocess_one(a, idx, v, g, vc.row(v)) : 0u;
     if (rect) {
         const int minx = rect & 0xff, miny = (rect >> 8) & 0xff, maxx = (rect >> 16) & 0xff, maxy = rect >> 24;
         if (use_smem) {

@@ -26,16 +26,17 @@ __device__ __forceinline__ void emit(float* p, float v, int atomic) {
 #define DM4D_PREBWD_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(DM4D_BLOCK, DM4D_PREBWD_MIN_BLOCKS) preprocess_backward_kernel(PreBwdArgs b) {
-    __shared__ ViewCache vc;
+    __shared__ ViewCache vcache;
+    ViewRows vc;
     const PreArgs& a = b.f;
     const long long first = (long long)blockIdx.x * blockDim.x;
     const long long idx = first + threadIdx.x;
-    vc.fill(a.view_params, (int)(first / a.P), a.n_views);
+    vc.fill(&vcache, a.view_params, (int)(first / a.P), a.n_views);
     __syncthreads();
     if (idx >= (long long)a.n_views * a.P) return;
     int v, g;
     split_index(first, threadIdx.x, a.P, v, g);
-    const float* __restrict__ vp = vc.row(a.view_params, v);
+    const float* __restrict__ vp = vc.row(v);
     const long long set = min(max((long long)vp[DM4D_VIEW_SET], 0ll), (long long)a.n_sets - 1);
     const bool live = a.g_rect[idx] != 0u;
     const float* acc = b.accum + (size_t)idx * a.acc;

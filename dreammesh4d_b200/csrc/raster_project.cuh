@@ -105,16 +105,21 @@ __device__ __forceinline__ bool project_gaussian(const float* __restrict__ vp, f
 // P >= blockDim, so both parameter rows are staged in shared memory once (the kernels read ~40 of the 48 floats per
 // thread; as global loads they were 48 LDG per thread).  Returns the row of view v (shared or global).
 struct ViewCache {
-    float rows[2][DM4D_VIEW_STRIDE];
+    float rows[2][DM4D_VIEW_STRIDE];       // the only shared state; (v_first, n) are block-uniform register values
+};
+struct ViewRows {
+    const ViewCache* vc;
+    const float* view_params;
     int v_first, n;
-    __device__ __forceinline__ void fill(const float* __restrict__ view_params, int v_first_, int n_views) {
-        v_first = v_first_;
+    // call from every thread of the block, then __syncthreads()
+    __device__ __forceinline__ void fill(ViewCache* cache, const float* __restrict__ vp, int v_first_, int n_views) {
+        vc = cache; view_params = vp; v_first = v_first_;
         n = min(2, n_views - v_first_);
-        for (int i = threadIdx.x; i < n * DM4D_VIEW_STRIDE; i += blockDim.x) rows[0][i] = view_params[(size_t)v_first_ * DM4D_VIEW_STRIDE + i];
+        for (int i = threadIdx.x; i < n * DM4D_VIEW_STRIDE; i += blockDim.x) cache->rows[0][i] = vp[(size_t)v_first_ * DM4D_VIEW_STRIDE + i];
     }
-    __device__ __forceinline__ const float* row(const float* __restrict__ view_params, int v) const {
+    __device__ __forceinline__ const float* row(int v) const {
         const int k = v - v_first;
-        return k < n ? rows[k] : view_params + (size_t)v * DM4D_VIEW_STRIDE;
+        return k < n ? vc->rows[k] : view_params + (size_t)v * DM4D_VIEW_STRIDE;
     }
 };
 
