@@ -23,6 +23,14 @@
 namespace {
 
 constexpr int VEC = 4;                 // channels per thread per access (8 B for fp16, 16 B for fp32)
+
+// SMs of the current device (148 on a B200).  The persistent kernels below bound their grids by the RESIDENT capacity
+// (SMs x occupancy): statically assigned work items must never sit behind CTAs that spin on them.
+int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    return n;
+}
 constexpr int MAX_GROUPS = 64;
 
 template <typename T> struct Vec4;
@@ -324,7 +332,7 @@ int launch_fused(const NormArgs& a, int threads, dim3 grid, const void* x, const
     const int total = 2 * a.N * f.slabs;
     int per_sm = 0;
     DM4D_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel<T, BWD>, threads, 0));
-    const unsigned blocks = (unsigned)std::min(total, 148 * std::max(1, per_sm));
+    const unsigned blocks = (unsigned)std::min(total, sm_count() * std::max(1, per_sm));
     {
         KernelTimer kt(BWD ? DM4D_K_GROUPNORM_BWD : DM4D_K_GROUPNORM_FWD, s);
         gn_fused_kernel<T, BWD><<<blocks, threads, 0, s>>>(f, (const T*)x, cb, (const T*)dy, gamma, beta, stats, (T*)out);
@@ -342,9 +350,10 @@ int forward_t(const NormArgs& a, int threads, dim3 grid, const void* x, const fl
         int& per_sm = per_sm_cache[threads / 32];
         if (per_sm == 0) DM4D_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_resident_kernel, threads, 0));
         const int k = threads / a.cvec;
-        const int slabs = std::min((a.HW + k - 1) / k, std::max(1, 148 * per_sm / a.N));
+        const int sms = sm_count();
+        const int slabs = std::min((a.HW + k - 1) / k, std::max(1, sms * per_sm / a.N));
         const int rows = (a.HW + slabs - 1) / slabs;
-        if (a.N * slabs <= 148 * per_sm && (rows + k - 1) / k <= RES_IT) {
+        if (a.N * slabs <= sms * per_sm && (rows + k - 1) / k <= RES_IT) {
             FusedArgs f;
             f.a = a;
             f.a.rows_per_block = rows;

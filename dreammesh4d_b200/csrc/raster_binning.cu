@@ -523,8 +523,16 @@ int launch_sort_pack_t(const RasterLayout& L, cudaStream_t s) {
     // The four tiers are independent: fork them onto side streams (works inside a stream capture too — the side
     // streams join the capture through the events), so the few CTAs of the heavy tiers (one 10^4-key tile takes a
     // 1024-thread CTA ~0.1 ms) run under the bulk of the small tiles instead of in front of them.
-    static cudaStream_t side[3] = {nullptr, nullptr, nullptr};
-    static cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+    // one set of side streams / events per device (one process per GPU is the design, but a process may own several)
+    constexpr int MAX_DEV = 16;
+    static cudaStream_t side_all[MAX_DEV][3] = {};
+    static cudaEvent_t fork_all[MAX_DEV] = {}, join_all[MAX_DEV][3] = {};
+    int dev = 0;
+    DM4D_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEV) { dm4d_set_error("sort_pack: device ordinal %d out of range", dev); return DM4D_EINVAL; }
+    cudaStream_t* side = side_all[dev];
+    cudaEvent_t& fork_ev = fork_all[dev];
+    cudaEvent_t* join_ev = join_all[dev];
     if (!fork_ev) {
         for (int i = 0; i < 3; ++i) {
             DM4D_CUDA_CHECK(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
