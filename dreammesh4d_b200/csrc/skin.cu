@@ -191,6 +191,9 @@ struct SkinBwdK {
     const float* g_means; const float* g_rots; const float* g_normals;
     float* dverts; float* dvert_rot;                       // scratch [n_t,V,4] each: gradients arriving from the faces
     const float* dverts_in; const float* dvert_rot_in;     // optional direct gradients [n_t,V,3] / [n_t,V,4]
+    // vertex-centric mode (all three or none): the Gaussian stage writes one 32-byte record per (t, face corner) and the
+    // vertex stage gathers them through the vertex -> corner lists: no reductions, no memset, reproducible order
+    const int32_t* vinc_ptr; const int32_t* vinc; float* corner;
     float* dn_trans; float* dn_rot; float* dn_scale; float* dn_opac;
 };
 
@@ -204,8 +207,19 @@ __device__ __forceinline__ void vertex_upstream(const SkinBwdK& a, int t, int v,
     const dm4d_skin_desc& d = a.d;
     const long long idx = (long long)t * d.V + v;
     const f3 x = ld3(d.rest_verts + (size_t)v * 3);
-    f3 gx = vec(ldq(a.dverts + (size_t)idx * 4));
-    float4 gr = ldq(a.dvert_rot + (size_t)idx * 4);
+    f3 gx = mk3(0, 0, 0);
+    float4 gr = make_float4(0, 0, 0, 0);
+    if (a.corner) {
+        const float* ct = a.corner + (size_t)t * d.F * 3 * 8;
+        for (int i = a.vinc_ptr[v]; i < a.vinc_ptr[v + 1]; ++i) {
+            const float* rec = ct + (size_t)a.vinc[i] * 8;
+            gx = gx + vec(ldq(rec));
+            gr = gr + ldq(rec + 4);
+        }
+    } else {
+        gx = vec(ldq(a.dverts + (size_t)idx * 4));
+        gr = ldq(a.dvert_rot + (size_t)idx * 4);
+    }
     if (a.dverts_in) gx = gx + ld3(a.dverts_in + (size_t)idx * 3);
     if (a.dvert_rot_in) gr = gr + ldq(a.dvert_rot_in + (size_t)idx * 4);
     VertSums s;
@@ -459,6 +473,28 @@ __global__ void __launch_bounds__(1024) incidence_scan_kernel(const int32_t* cou
     }
     if (threadIdx.x == 0) inc_ptr[M] = carry;
 }
+// Many short lists (vertex -> face corners: ~6 entries each, V lists): scatter with per-list cursors, then every list is
+// sorted by one thread (insertion sort) so the order — and with it every floating-point sum over a list — is reproducible.
+__global__ void __launch_bounds__(DM4D_BLOCK) incidence_scatter_kernel(const int32_t* idx, int n, int M, const int32_t* inc_ptr,
+                                                                       int32_t* cursor, int32_t* inc) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int node = idx[e];
+    if (node < 0 || node >= M) return;
+    inc[inc_ptr[node] + atomicAdd(cursor + node, 1)] = e;
+}
+__global__ void __launch_bounds__(DM4D_BLOCK) incidence_sort_lists_kernel(int M, const int32_t* inc_ptr, int32_t* inc) {
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= M) return;
+    const int lo = inc_ptr[node], hi = inc_ptr[node + 1];
+    for (int i = lo + 1; i < hi; ++i) {
+        const int32_t key = inc[i];
+        int j = i - 1;
+        while (j >= lo && inc[j] > key) { inc[j + 1] = inc[j]; --j; }
+        inc[j + 1] = key;
+    }
+}
+
 __global__ void __launch_bounds__(DM4D_BLOCK) incidence_fill_kernel(const int32_t* nbr_idx, int n, int M, const int32_t* inc_ptr, int32_t* inc) {
     const int node = blockIdx.x * (DM4D_BLOCK / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (node >= M) return;
@@ -641,8 +677,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK, 3) skin_gaussian_backward_kernel(S
                 for (int k = 0; k < 3; ++k) dL[k] = dL[k] + b[k] * dxi;
             }
     }
-    if (!live) return;
-    if (a.g_normals) {
+    if (live && a.g_normals) {
         const f3 e1 = x[1] - x[0], e2 = x[2] - x[0];
         const f3 c = cross(e1, e2);
         const float len = sqrtf(dot(c, c));
@@ -659,6 +694,24 @@ __global__ void __launch_bounds__(DM4D_BLOCK, 3) skin_gaussian_backward_kernel(S
         dx[1] = dx[1] + de1;
         dx[2] = dx[2] + de2;
     }
+    if (a.corner) {
+        // vertex-centric mode: the warp's 32 x 3 corner records (8 floats each = exactly the staging buffer) leave as one
+        // contiguous block; the vertex stage gathers them
+        __syncwarp();
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 dr = a.g_rots ? so3_log_bwd(r[k], dL[k]) : make_float4(0, 0, 0, 0);
+                float4* rec = reinterpret_cast<float4*>(st + (lane * 3 + k) * 8);
+                rec[0] = make_float4(dx[k].x, dx[k].y, dx[k].z, 0.f);
+                rec[1] = dr;
+            }
+        }
+        __syncwarp();
+        warp_store_block(a.corner + (size_t)wfirst * 24, st, cnt * 24, lane);
+        return;
+    }
+    if (!live) return;
     // one 16-byte vector reduction per corner and quantity (the scratch rows are padded to float4)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -858,14 +911,23 @@ extern "C" int dm4d_skin_backward(const dm4d_skin_desc* d, const float* verts, c
         dm4d_set_error("skin backward: dverts / dvert_rot must be 16-byte aligned");
         return DM4D_EINVAL;
     }
-    DM4D_CUDA_CHECK(cudaMemsetAsync(dverts, 0, nv * 4 * sizeof(float), s));
-    DM4D_CUDA_CHECK(cudaMemsetAsync(dvert_rot, 0, nv * 4 * sizeof(float), s));
+    const int n_vc = (d->vert_inc_ptr != nullptr) + (d->vert_inc != nullptr) + (d->corner_scratch != nullptr);
+    if (n_vc != 0 && n_vc != 3) { dm4d_set_error("skin backward: vert_inc_ptr, vert_inc and corner_scratch go together"); return DM4D_EINVAL; }
+    if (n_vc == 3 && (reinterpret_cast<uintptr_t>(d->corner_scratch) & 15)) { dm4d_set_error("skin backward: corner_scratch must be 16-byte aligned"); return DM4D_EINVAL; }
+    const bool any_gauss_grad = dL_dmeans3D || dL_drotations || dL_dnormals;
+    if (n_vc == 0) {
+        DM4D_CUDA_CHECK(cudaMemsetAsync(dverts, 0, nv * 4 * sizeof(float), s));
+        DM4D_CUDA_CHECK(cudaMemsetAsync(dvert_rot, 0, nv * 4 * sizeof(float), s));
+    } else if (!any_gauss_grad) {
+        DM4D_CUDA_CHECK(cudaMemsetAsync(d->corner_scratch, 0, nf * 3 * 8 * sizeof(float), s));   // the gather must read zeros
+    }
     SkinBwdK a;
     a.d = *d; a.P = d->F * d->g;
     a.verts = verts; a.vert_rot = vert_rot;
     a.g_means = dL_dmeans3D; a.g_rots = dL_drotations; a.g_normals = dL_dnormals;
     a.dverts = dverts; a.dvert_rot = dvert_rot;
     a.dverts_in = dL_dverts_in; a.dvert_rot_in = dL_dvert_rot_in;
+    a.vinc_ptr = d->vert_inc_ptr; a.vinc = d->vert_inc; a.corner = d->corner_scratch;
     a.dn_trans = dL_dnode_trans; a.dn_rot = dL_dnode_rot; a.dn_scale = dL_dnode_scale; a.dn_opac = dL_dnode_opacity;
     if (dL_dmeans3D || dL_drotations || dL_dnormals) {
         KernelTimer kt(DM4D_K_SKIN_GAUSS_BWD, s);
@@ -910,8 +972,16 @@ extern "C" int dm4d_skin_node_incidence(const int32_t* nbr_idx, int32_t V, int32
     DM4D_CUDA_CHECK(cudaMemsetAsync(scratch, 0, ((size_t)M + 1) * sizeof(int32_t), s));
     incidence_count_kernel<<<(n + DM4D_BLOCK - 1) / DM4D_BLOCK, DM4D_BLOCK, 0, s>>>(nbr_idx, n, M, scratch, scratch + M);
     incidence_scan_kernel<<<1, 1024, 0, s>>>(scratch, M, inc_ptr);
-    const int per = DM4D_BLOCK / 32;
-    incidence_fill_kernel<<<(M + per - 1) / per, DM4D_BLOCK, 0, s>>>(nbr_idx, n, M, inc_ptr, inc);
+    if ((long long)n <= 64ll * M) {
+        // many short lists (e.g. vertex -> face corners): scatter + per-list sort
+        DM4D_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)M * sizeof(int32_t), s));
+        incidence_scatter_kernel<<<(n + DM4D_BLOCK - 1) / DM4D_BLOCK, DM4D_BLOCK, 0, s>>>(nbr_idx, n, M, inc_ptr, scratch, inc);
+        incidence_sort_lists_kernel<<<(M + DM4D_BLOCK - 1) / DM4D_BLOCK, DM4D_BLOCK, 0, s>>>(M, inc_ptr, inc);
+    } else {
+        // few long lists (control nodes): one warp per list compacts the entries in order
+        const int per = DM4D_BLOCK / 32;
+        incidence_fill_kernel<<<(M + per - 1) / per, DM4D_BLOCK, 0, s>>>(nbr_idx, n, M, inc_ptr, inc);
+    }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }

@@ -22,9 +22,11 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 
 _INCIDENCE: dict = {}
-USE_NODE_INCIDENCE = True     # node-centric backward over incidence lists (no atomics on the node tables, reproducible
-                              # summation order; 226 us at C5 x 8 timestamps); False: the C ABI's list-free backward
-                              # (warp-aggregated floating-point reductions, 428 us there)
+USE_NODE_INCIDENCE = True     # node-centric vertex backward over incidence lists (node -> vertex slots): no reductions into
+                              # the node tables; False: the C ABI's list-free backward (warp-aggregated reductions)
+REPRODUCIBLE = False          # True: also gather the face -> vertex gradients through vertex -> corner lists instead of
+                              # 16-byte vector reductions: the whole backward is bit-reproducible, ~10 % slower (C5: 672 vs
+                              # 612 us at 8 timestamps)
 
 
 def node_incidence(nbr_idx: torch.Tensor, M: int):
@@ -84,6 +86,10 @@ class _SkinFunction(torch.autograd.Function):
             inc_ptr, inc = node_incidence(keep[2], M)
             d.node_inc_ptr, d.node_inc = ptr(inc_ptr), ptr(inc)
             keep += [inc_ptr, inc]
+            if REPRODUCIBLE:
+                vinc_ptr, vinc = node_incidence(keep[1], V)      # vertex -> face corners (same builder, K = 3)
+                d.vert_inc_ptr, d.vert_inc = ptr(vinc_ptr), ptr(vinc)
+                keep += [vinc_ptr, vinc]
         f32 = dict(dtype=torch.float32, device=dev)
         verts = torch.empty(T, V, 3, **f32)
         vert_rot = torch.empty(T, V, 4, **f32)
@@ -121,6 +127,9 @@ class _SkinFunction(torch.autograd.Function):
         if d.node_inc:
             scratch = torch.empty(T, V, 16, **f32)
             d.vert_scratch = ptr(scratch)
+        if d.vert_inc:
+            corner = torch.empty(T, d.F * 3, 8, **f32)
+            d.corner_scratch = ptr(corner)
         check(l.dm4d_skin_backward(ctypes.byref(d), ptr(verts), ptr(vert_rot), ptr(g_means), ptr(g_rots),
                                    ptr(g_normals), ptr(g_verts), ptr(g_vert_rot), ptr(dverts), ptr(dvrot), ptr(dn_t),
                                    ptr(dn_r), ptr(dn_s), ptr(dn_o), torch.cuda.current_stream().cuda_stream),

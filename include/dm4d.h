@@ -181,10 +181,21 @@ typedef struct dm4d_skin_desc {
     const int32_t* node_inc_ptr; /* [M+1] */
     const int32_t* node_inc;     /* [V*K] flat (vertex, slot) indices e = v*K + k, grouped by node, ascending */
     float* vert_scratch;         /* [n_t, V, 16] caller-owned scratch, 16-byte aligned (overwritten) */
+    /* Optional (backward only; all three or none): the vertices' incidence lists over the face corners
+     * (dm4d_skin_node_incidence(faces, F, 3, V, ...): flat corner indices e = f*3 + c grouped by vertex, ascending) and a
+     * scratch buffer.  With them the Gaussian stage writes one 32-byte gradient record per (timestamp, face corner) and the
+     * vertex stage gathers them: no floating-point reductions into the per-vertex rows, reproducible summation order
+     * (with the node lists above the whole backward is bit-reproducible; ~10 % slower at C5).  Without them: 16-byte
+     * vector reductions (the default of the Python host side). */
+    const int32_t* vert_inc_ptr; /* [V+1] */
+    const int32_t* vert_inc;     /* [F*3] */
+    float* corner_scratch;       /* [n_t, F*3, 8] caller-owned scratch, 16-byte aligned (overwritten) */
 } dm4d_skin_desc;
 
-/* Incidence lists of the deformation graph (start-up; the graph of dynamic_sugar.py:745-861 is fixed afterwards):
- * inc_ptr [M+1], inc [V*K] as described above.  scratch: [M+1] int32; scratch[M] != 0 afterwards means that nbr_idx
+/* Incidence lists (start-up; the deformation graph of dynamic_sugar.py:745-861 and the mesh are fixed afterwards): for an
+ * index table nbr_idx [V, K] with values in [0, M) — the control nodes of every vertex, or the three vertices of every
+ * face (V := F, K := 3, M := number of vertices) — the flat positions e = v*K + k grouped by value, ascending:
+ * inc_ptr [M+1], inc [V*K].  scratch: [M+1] int32; scratch[M] != 0 afterwards means that nbr_idx
  * held an index outside [0, M) (the lists are then incomplete). */
 int dm4d_skin_node_incidence(const int32_t* nbr_idx, int32_t V, int32_t K, int32_t M, int32_t* inc_ptr, int32_t* inc,
                              int32_t* scratch, void* stream);
