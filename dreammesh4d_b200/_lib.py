@@ -47,7 +47,7 @@ class SkinDesc(ctypes.Structure):
         ("rest_verts", c_void_p), ("faces", c_void_p), ("nbr_idx", c_void_p), ("nbr_w", c_void_p),
         ("bary", c_void_p), ("rest_quat", c_void_p), ("node_trans", c_void_p), ("node_rot", c_void_p),
         ("node_scale", c_void_p), ("node_opacity", c_void_p), ("node_inc_ptr", c_void_p), ("node_inc", c_void_p), ("vert_scratch", c_void_p),
-        ("vert_inc_ptr", c_void_p), ("vert_inc", c_void_p), ("corner_scratch", c_void_p),
+        ("vert_inc_ptr", c_void_p), ("vert_inc", c_void_p), ("corner_scratch", c_void_p), ("node_scratch", c_void_p),
     ]
 
 

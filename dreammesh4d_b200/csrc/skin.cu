@@ -98,6 +98,29 @@ __device__ __forceinline__ float4 so3_exp(f3 x) {
     else { a = 0.5f - th2 / 48.f + th2 * th2 / 3840.f; w = 1.f - th2 / 8.f + th2 * th2 / 384.f; }
     return mkq(a * x, w);
 }
+// exp and the three coefficients of its derivative from ONE sincos evaluation (the backward of the Gaussian stage needs
+// both for every Gaussian: dq = exp(xi) to rebuild the rotation, d exp / d xi to differentiate it)
+struct ExpBwdCoef { float a, da_over_th, dw_coef; };
+__device__ __forceinline__ float4 so3_exp_coef(f3 x, ExpBwdCoef& c) {
+    const float th2 = dot(x, x), th = sqrtf(th2);
+    float w;
+    if (th > EPS_LIE) {
+        float sn, cs;
+        sincosf(0.5f * th, &sn, &cs);
+        c.a = sn / th; w = cs;
+        c.da_over_th = (0.5f * cs * th - sn) / (th2 * th);
+        c.dw_coef = -0.5f * c.a;
+    } else {
+        c.a = 0.5f - th2 / 48.f + th2 * th2 / 3840.f; w = 1.f - th2 / 8.f + th2 * th2 / 384.f;
+        c.da_over_th = -1.f / 24.f + th2 / 960.f;
+        c.dw_coef = -0.25f + th2 / 96.f;
+    }
+    return mkq(c.a * x, w);
+}
+__device__ __forceinline__ f3 so3_exp_bwd_apply(ExpBwdCoef c, f3 x, float4 g) {
+    const f3 gv = vec(g);
+    return c.a * gv + (dot(gv, x) * c.da_over_th + g.w * c.dw_coef) * x;
+}
 // dL/dx given g = dL/d(exp x) (xyzw)
 __device__ __forceinline__ f3 so3_exp_bwd(f3 x, float4 g) {
     const float th2 = dot(x, x), th = sqrtf(th2);
@@ -134,8 +157,31 @@ struct VertSums {
     f3 x_l; float4 sq_r, sq_d; float lam_raw; f3 xi;
 };
 
+// Per-(timestamp, node) quantities every (vertex, neighbour) pair needs: log of the node rotation, its normalised
+// quaternion and the dual part — an atan, a reciprocal square root and a quaternion product per PAIR when evaluated
+// inline.  With desc.node_scratch a pre-pass of n_t * M threads evaluates them once: 3 float4 per (t, node).
+__device__ __forceinline__ void node_pre_eval(int method, f3 tr, float4 q, f3& nlog, float4& qn, float4& qd) {
+    nlog = so3_log(q);
+    qn = make_float4(0, 0, 0, 0); qd = qn;
+    if (method != 0) {
+        const float inv = 1.f / sqrtf(dot4(q, q));
+        qn = inv * q;
+        qd = qmul(mkq(0.5f * tr, 0.f), qn);
+    }
+}
+__global__ void __launch_bounds__(DM4D_BLOCK) skin_node_pre_kernel(dm4d_skin_desc d, float4* __restrict__ pre) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n_t * d.M) return;
+    f3 nlog; float4 qn, qd;
+    node_pre_eval(d.method, ld3(d.node_trans + (size_t)i * 3), ldq(d.node_rot + (size_t)i * 4), nlog, qn, qd);
+    pre[(size_t)i * 3] = mkq(nlog, 0.f);
+    pre[(size_t)i * 3 + 1] = qn;
+    pre[(size_t)i * 3 + 2] = qd;
+}
+
 __device__ __forceinline__ void vertex_accumulate(const dm4d_skin_desc& d, int t, int v, f3 x, VertSums& s) {
     s.x_l = mk3(0, 0, 0); s.sq_r = make_float4(0, 0, 0, 0); s.sq_d = make_float4(0, 0, 0, 0); s.lam_raw = 0.f; s.xi = mk3(0, 0, 0);
+    const float4* pre = reinterpret_cast<const float4*>(d.node_scratch);
     for (int k = 0; k < d.K; ++k) {
         const int n = d.nbr_idx[(size_t)v * d.K + k];
         const float w = d.nbr_w[(size_t)v * d.K + k];
@@ -147,15 +193,19 @@ __device__ __forceinline__ void vertex_accumulate(const dm4d_skin_desc& d, int t
             const f3 y = mk3(S[0] * x.x + S[1] * x.y + S[2] * x.z, S[3] * x.x + S[4] * x.y + S[5] * x.z, S[6] * x.x + S[7] * x.y + S[8] * x.z);
             s.x_l = s.x_l + w * (qact(q, y) + tr);
         }
+        f3 nlog; float4 qn, qd;
+        if (pre) {
+            nlog = vec(pre[base * 3]);
+            if (d.method != 0) { qn = pre[base * 3 + 1]; qd = pre[base * 3 + 2]; }
+        } else {
+            node_pre_eval(d.method, tr, q, nlog, qn, qd);
+        }
         if (d.method != 0) {
-            const float inv = 1.f / sqrtf(dot4(q, q));
-            const float4 qn = inv * q;
-            const float4 qd = qmul(mkq(0.5f * tr, 0.f), qn);
             s.sq_r = s.sq_r + w * qn;
             s.sq_d = s.sq_d + w * qd;
         }
         if (d.method == 2) s.lam_raw += w * d.node_opacity[base];
-        s.xi = s.xi + w * so3_log(q);
+        s.xi = s.xi + w * nlog;
     }
 }
 
@@ -627,13 +677,15 @@ __global__ void __launch_bounds__(DM4D_BLOCK, 3) skin_gaussian_backward_kernel(S
     const size_t vb = (size_t)t * d.V;
     f3 x[3], L[3];
     float4 r[3];
+    LogBwdCoef lc[3];                 // log and its derivative share the atan
     if (live) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             vi[k] = d.faces[(size_t)f * 3 + k];
             x[k] = ld3(a.verts + (vb + vi[k]) * 3);
             r[k] = ldq(a.vert_rot + (vb + vi[k]) * 4);
-            L[k] = so3_log(r[k]);
+            lc[k] = so3_log_bwd_coef(r[k]);
+            L[k] = lc[k].f * vec(r[k]);
         }
     }
     f3 dx[3] = {mk3(0, 0, 0), mk3(0, 0, 0), mk3(0, 0, 0)};
@@ -664,7 +716,8 @@ __global__ void __launch_bounds__(DM4D_BLOCK, 3) skin_gaussian_backward_kernel(S
             for (int j = 0; j < g; ++j) {
                 const float b[3] = {d.bary[j * 3], d.bary[j * 3 + 1], d.bary[j * 3 + 2]};
                 const f3 xi = b[0] * L[0] + b[1] * L[1] + b[2] * L[2];
-                const float4 dq = so3_exp(xi);
+                ExpBwdCoef ec;
+                const float4 dq = so3_exp_coef(xi, ec);
                 const float4 rest = wxyz_to_xyzw(ldq(d.rest_quat + ((size_t)f * g + j) * 4));
                 const float4 u = qmul(dq, rest);                         // xyzw
                 const float nu = fmaxf(sqrtf(dot4(u, u)), 1e-12f), inv = 1.f / nu;
@@ -672,7 +725,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK, 3) skin_gaussian_backward_kernel(S
                 const float4 gq = wxyz_to_xyzw(*reinterpret_cast<const float4*>(st + (lane * g + j) * 4));  // incoming gradient is wxyz
                 const float4 du = inv * (gq + (-dot4(qn, gq)) * qn);
                 const float4 ddq = qmul(du, qconj(rest));
-                const f3 dxi = so3_exp_bwd(xi, ddq);
+                const f3 dxi = so3_exp_bwd_apply(ec, xi, ddq);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) dL[k] = dL[k] + b[k] * dxi;
             }
@@ -701,7 +754,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK, 3) skin_gaussian_backward_kernel(S
         if (live) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float4 dr = a.g_rots ? so3_log_bwd(r[k], dL[k]) : make_float4(0, 0, 0, 0);
+                const float4 dr = a.g_rots ? so3_log_bwd_apply(lc[k], r[k], dL[k]) : make_float4(0, 0, 0, 0);
                 float4* rec = reinterpret_cast<float4*>(st + (lane * 3 + k) * 8);
                 rec[0] = make_float4(dx[k].x, dx[k].y, dx[k].z, 0.f);
                 rec[1] = dr;
@@ -717,7 +770,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK, 3) skin_gaussian_backward_kernel(S
     for (int k = 0; k < 3; ++k) {
         red_add_v4(a.dverts + (vb + vi[k]) * 4, dx[k].x, dx[k].y, dx[k].z, 0.f);
         if (a.g_rots) {
-            const float4 dr = so3_log_bwd(r[k], dL[k]);
+            const float4 dr = so3_log_bwd_apply(lc[k], r[k], dL[k]);
             red_add_v4(a.dvert_rot + (vb + vi[k]) * 4, dr.x, dr.y, dr.z, dr.w);
         }
     }
@@ -886,6 +939,10 @@ extern "C" int dm4d_skin_forward(const dm4d_skin_desc* d, float* verts, float* v
     a.d = *d; a.P = d->F * d->g;
     a.verts = verts; a.vert_rot = vert_rot; a.means = means3D; a.rots = rotations; a.normals = normals;
     const long long nv = (long long)d->n_t * d->V, nf = (long long)d->n_t * d->F;
+    if (d->node_scratch) {
+        if (reinterpret_cast<uintptr_t>(d->node_scratch) & 15) { dm4d_set_error("skin: node_scratch must be 16-byte aligned"); return DM4D_EINVAL; }
+        skin_node_pre_kernel<<<(unsigned)((d->n_t * d->M + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(*d, reinterpret_cast<float4*>(d->node_scratch));
+    }
     { KernelTimer kt(DM4D_K_SKIN_VERT_FWD, s); skin_vertex_forward_kernel<<<(unsigned)((nv + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(a); }
     DM4D_CUDA_CHECK(cudaGetLastError());
     { KernelTimer kt(DM4D_K_SKIN_GAUSS_FWD, s); skin_gaussian_forward_kernel<<<(unsigned)((nf + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(a); }
@@ -929,6 +986,10 @@ extern "C" int dm4d_skin_backward(const dm4d_skin_desc* d, const float* verts, c
     a.dverts_in = dL_dverts_in; a.dvert_rot_in = dL_dvert_rot_in;
     a.vinc_ptr = d->vert_inc_ptr; a.vinc = d->vert_inc; a.corner = d->corner_scratch;
     a.dn_trans = dL_dnode_trans; a.dn_rot = dL_dnode_rot; a.dn_scale = dL_dnode_scale; a.dn_opac = dL_dnode_opacity;
+    if (d->node_scratch) {           // same pre-pass as the forward (the caller may have reused the scratch in between)
+        if (reinterpret_cast<uintptr_t>(d->node_scratch) & 15) { dm4d_set_error("skin: node_scratch must be 16-byte aligned"); return DM4D_EINVAL; }
+        skin_node_pre_kernel<<<(unsigned)((d->n_t * d->M + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(*d, reinterpret_cast<float4*>(d->node_scratch));
+    }
     if (dL_dmeans3D || dL_drotations || dL_dnormals) {
         KernelTimer kt(DM4D_K_SKIN_GAUSS_BWD, s);
         skin_gaussian_backward_kernel<<<(unsigned)((nf + DM4D_BLOCK - 1) / DM4D_BLOCK), DM4D_BLOCK, 0, s>>>(a);

@@ -91,6 +91,9 @@ class _SkinFunction(torch.autograd.Function):
                 d.vert_inc_ptr, d.vert_inc = ptr(vinc_ptr), ptr(vinc)
                 keep += [vinc_ptr, vinc]
         f32 = dict(dtype=torch.float32, device=dev)
+        node_pre = torch.empty(T, M, 12, **f32)                  # per-(timestamp, node) pre-pass table
+        d.node_scratch = ptr(node_pre)
+        keep.append(node_pre)
         verts = torch.empty(T, V, 3, **f32)
         vert_rot = torch.empty(T, V, 4, **f32)
         means = torch.empty(T, P, 3, **f32)

@@ -190,6 +190,10 @@ typedef struct dm4d_skin_desc {
     const int32_t* vert_inc_ptr; /* [V+1] */
     const int32_t* vert_inc;     /* [F*3] */
     float* corner_scratch;       /* [n_t, F*3, 8] caller-owned scratch, 16-byte aligned (overwritten) */
+    /* Optional (forward and backward): [n_t, M, 12] scratch, 16-byte aligned (overwritten by every call).  With it the
+     * per-node quantities every (vertex, neighbour) pair needs (rotation log, normalised quaternion, dual part) are
+     * evaluated once per (timestamp, node) in a pre-pass instead of once per pair. */
+    float* node_scratch;
 } dm4d_skin_desc;
 
 /* Incidence lists (start-up; the deformation graph of dynamic_sugar.py:745-861 and the mesh are fixed afterwards): for an
