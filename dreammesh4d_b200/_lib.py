@@ -36,6 +36,7 @@ class RasterDesc(ctypes.Structure):
         ("img", c_void_p), ("img_bytes", c_uint64),
         ("bwd", c_void_p), ("bwd_bytes", c_uint64),
         ("bin_capacity", c_int64),
+        ("cov3D", c_void_p), ("cov3D_stride", c_int64), ("dL_dcov3D", c_void_p),
     ]
 
 

@@ -45,7 +45,7 @@ int raster_make_layout(const dm4d_raster_desc* d, RasterLayout* L) {
     if (gx > 255 || gy > 255) { dm4d_set_error("image too large: %dx%d tiles (max 255 per side)", gx, gy); return DM4D_EINVAL; }
     if (d->bin_capacity < 0 || d->bin_capacity >= (1ll << 31)) { dm4d_set_error("bin_capacity out of range"); return DM4D_EINVAL; }
     if ((long long)d->n_views * d->P >= (1ll << 31)) { dm4d_set_error("n_views*P too large"); return DM4D_EINVAL; }
-    if (d->P > 0 && (!d->means3D || !d->scales || !d->rotations || !d->opacities || !d->colors || !d->view_params ||
+    if (d->P > 0 && (!d->means3D || (!d->cov3D && (!d->scales || !d->rotations)) || !d->opacities || !d->colors || !d->view_params ||
                      (d->channels == 6 && !d->colors2))) {
         dm4d_set_error("NULL input pointer");
         return DM4D_EINVAL;

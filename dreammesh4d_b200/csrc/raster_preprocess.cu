@@ -20,16 +20,19 @@ __device__ __forceinline__ unsigned int preprocess_one(const PreArgs& a, long lo
     a.g_rect[idx] = 0u;
 
     const float* m = a.means3D + set * a.means3D_stride + (size_t)g * 3;
-    const float* sc = a.scales + set * a.scales_stride + (size_t)g * 3;
-    const float4 q = load_quat(a.rotations + set * a.rotations_stride + (size_t)g * 4);
-    const float mod = vp[DM4D_VIEW_SCALE_MOD];
     const float focal_x = (float)a.W / (2.0f * vp[DM4D_VIEW_TANFOVX]);
     const float focal_y = (float)a.H / (2.0f * vp[DM4D_VIEW_TANFOVY]);
 
     Proj pr;
-    if (!project_gaussian(vp, m[0], m[1], m[2], mod * sc[0], mod * sc[1], mod * sc[2], q.x, q.y, q.z, q.w,
-                          focal_x, focal_y, pr))
-        return 0u;
+    if (a.cov3D) {
+        load_sigma(a.cov3D + set * a.cov3D_stride + (size_t)g * 6, pr.S);
+    } else {
+        const float* sc = a.scales + set * a.scales_stride + (size_t)g * 3;
+        const float4 q = load_quat(a.rotations + set * a.rotations_stride + (size_t)g * 4);
+        const float mod = vp[DM4D_VIEW_SCALE_MOD];
+        gaussian_sigma(mod * sc[0], mod * sc[1], mod * sc[2], q.x, q.y, q.z, q.w, pr.S);
+    }
+    if (!project_with_sigma(vp, m[0], m[1], m[2], focal_x, focal_y, pr)) return 0u;
 
     const float det = pr.a * pr.c - pr.b * pr.b;
     if (det == 0.0f) return 0u;

@@ -15,6 +15,7 @@ struct PreBwdArgs {
     float* dopac;    int dopac_atomic;
     float* dscales;  int dscales_atomic;
     float* drots;    int drots_atomic;
+    float* dcov;     int dcov_atomic;
 };
 
 __device__ __forceinline__ void emit(float* p, float v, int atomic) {
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK, DM4D_PREBWD_MIN_BLOCKS) preprocess
     const float* acc = b.accum + (size_t)idx * a.acc;
 
     float dm[3] = {0.f, 0.f, 0.f}, ds[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
+    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float g2x = 0.f, g2y = 0.f, gop = 0.f;
     float gcol[DM4D_MAX_CHANNELS] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
@@ -55,16 +57,22 @@ __global__ void __launch_bounds__(DM4D_BLOCK, DM4D_PREBWD_MIN_BLOCKS) preprocess
         for (int ch = 0; ch < a.channels; ++ch) gcol[ch] = acc[8 + ch];
 
         const float* m = a.means3D + set * a.means3D_stride + (size_t)g * 3;
-        const float* sc = a.scales + set * a.scales_stride + (size_t)g * 3;
-        const float4 q4 = load_quat(a.rotations + set * a.rotations_stride + (size_t)g * 4);
-        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
         const float mod = vp[DM4D_VIEW_SCALE_MOD];
         const float fx = (float)a.W / (2.0f * vp[DM4D_VIEW_TANFOVX]);
         const float fy = (float)a.H / (2.0f * vp[DM4D_VIEW_TANFOVY]);
         const float px = m[0], py = m[1], pz = m[2];
-        const float s[3] = {mod * sc[0], mod * sc[1], mod * sc[2]};
+        float q[4] = {1.f, 0.f, 0.f, 0.f}, s[3] = {0.f, 0.f, 0.f};
         Proj pr;
-        project_gaussian(vp, px, py, pz, s[0], s[1], s[2], q[0], q[1], q[2], q[3], fx, fy, pr);
+        if (a.cov3D) {
+            load_sigma(a.cov3D + set * a.cov3D_stride + (size_t)g * 6, pr.S);
+        } else {
+            const float* sc = a.scales + set * a.scales_stride + (size_t)g * 3;
+            const float4 q4 = load_quat(a.rotations + set * a.rotations_stride + (size_t)g * 4);
+            q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
+            s[0] = mod * sc[0]; s[1] = mod * sc[1]; s[2] = mod * sc[2];
+            gaussian_sigma(s[0], s[1], s[2], q[0], q[1], q[2], q[3], pr.S);
+        }
+        project_with_sigma(vp, px, py, pz, fx, fy, pr);
         const float* V = vp;
         const float* PV = vp + 16;
 
@@ -111,6 +119,11 @@ __global__ void __launch_bounds__(DM4D_BLOCK, DM4D_PREBWD_MIN_BLOCKS) preprocess
             dm[k] += (V[2 + 4 * k] - V[3 + 4 * k] * pr.tz) * gd;
         }
 
+        if (a.cov3D) {
+            // gradient w.r.t. the six unique entries of the precomputed covariance (off-diagonal entries occur twice)
+            dcov[0] = GS[0][0]; dcov[1] = 2.f * GS[0][1]; dcov[2] = 2.f * GS[0][2];
+            dcov[3] = GS[1][1]; dcov[4] = 2.f * GS[1][2]; dcov[5] = GS[2][2];
+        } else {
         // (5) Sigma = L L^T, L = Rm diag(s)
         float Rm[3][3], L[3][3], dLm[3][3], dR[3][3];
         quat_to_R(q[0], q[1], q[2], q[3], Rm);
@@ -134,6 +147,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK, DM4D_PREBWD_MIN_BLOCKS) preprocess
         dq[1] = 2.f * (y * (dR[0][1] + dR[1][0]) + z * (dR[0][2] + dR[2][0]) + r * (dR[2][1] - dR[1][2])) - 4.f * x * (dR[1][1] + dR[2][2]);
         dq[2] = 2.f * (x * (dR[0][1] + dR[1][0]) + r * (dR[0][2] - dR[2][0]) + z * (dR[1][2] + dR[2][1])) - 4.f * y * (dR[0][0] + dR[2][2]);
         dq[3] = 2.f * (r * (dR[1][0] - dR[0][1]) + x * (dR[0][2] + dR[2][0]) + y * (dR[1][2] + dR[2][1])) - 4.f * z * (dR[0][0] + dR[1][1]);
+        }
     }
 
     if (b.dmeans2D) {
@@ -152,6 +166,10 @@ __global__ void __launch_bounds__(DM4D_BLOCK, DM4D_PREBWD_MIN_BLOCKS) preprocess
     if (b.drots && (live || !b.drots_atomic)) {
         float* o = b.drots + set * a.rotations_stride + (size_t)g * 4;
         for (int k = 0; k < 4; ++k) emit(o + k, dq[k], b.drots_atomic);
+    }
+    if (b.dcov && (live || !b.dcov_atomic)) {
+        float* o = b.dcov + set * a.cov3D_stride + (size_t)g * 6;
+        for (int k = 0; k < 6; ++k) emit(o + k, dcov[k], b.dcov_atomic);
     }
     if (b.dopac && (live || !b.dopac_atomic)) emit(b.dopac + set * a.opacities_stride + g, gop, b.dopac_atomic);
     if (b.dcolors && (live || !b.dcolors_atomic)) {
@@ -195,6 +213,8 @@ int launch_preprocess_backward(const dm4d_raster_desc* d, const RasterLayout& L,
     b.dopac = dL_dopacities;  b.dopac_atomic = mode(dL_dopacities, d->opacities_stride, P);
     b.dscales = dL_dscales;   b.dscales_atomic = mode(dL_dscales, d->scales_stride, P * 3);
     b.drots = dL_drotations;  b.drots_atomic = mode(dL_drotations, d->rotations_stride, P * 4);
+    b.dcov = d->cov3D ? d->dL_dcov3D : nullptr; b.dcov_atomic = mode(b.dcov, d->cov3D_stride, P * 6);
+    if (d->cov3D) { b.dscales = nullptr; b.drots = nullptr; }        // scales / rotations are not inputs of this call
     const unsigned blocks = (unsigned)((n + DM4D_BLOCK - 1) / DM4D_BLOCK);
     { KernelTimer kt(DM4D_K_PREPROCESS_BWD, s); preprocess_backward_kernel<<<blocks, DM4D_BLOCK, 0, s>>>(b); }
     DM4D_CUDA_CHECK(cudaGetLastError());

@@ -14,6 +14,7 @@ struct PreArgs {
     const float* opacities; long long opacities_stride;
     const float* colors;    long long colors_stride;
     const float* colors2;   long long colors2_stride;
+    const float* cov3D;     long long cov3D_stride;     // optional: precomputed 3D covariances instead of scales / rotations
     const float* view_params;
     float* g_rec;
     unsigned int* g_rect;
@@ -47,20 +48,8 @@ struct Proj {
     float xmul, ymul;          // 0 where the 1.3 tanfov clamp was active
 };
 
-__device__ __forceinline__ bool project_gaussian(const float* __restrict__ vp, float px, float py, float pz,
-                                                 float s0, float s1, float s2, float qr, float qx, float qy,
-                                                 float qz, float focal_x, float focal_y, Proj& o) {
-    const float* V = vp;
-    const float* PV = vp + 16;
-    o.tx = V[0] * px + V[4] * py + V[8] * pz + V[12];
-    o.ty = V[1] * px + V[5] * py + V[9] * pz + V[13];
-    o.tz = V[2] * px + V[6] * py + V[10] * pz + V[14];
-    if (o.tz <= 0.2f) return false;
-    o.hx = PV[0] * px + PV[4] * py + PV[8] * pz + PV[12];
-    o.hy = PV[1] * px + PV[5] * py + PV[9] * pz + PV[13];
-    o.hw = PV[3] * px + PV[7] * py + PV[11] * pz + PV[15];
-    o.p_w = 1.0f / (o.hw + 0.0000001f);
-
+// 3D covariance Sigma = L L^T, L = R(q) diag(s)
+__device__ __forceinline__ void gaussian_sigma(float s0, float s1, float s2, float qr, float qx, float qy, float qz, float (&S)[3][3]) {
     float Rm[3][3], L[3][3];
     quat_to_R(qr, qx, qy, qz, Rm);
     const float s[3] = {s0, s1, s2};
@@ -72,9 +61,30 @@ __device__ __forceinline__ bool project_gaussian(const float* __restrict__ vp, f
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int b = a; b < 3; ++b) {
-            o.S[a][b] = L[a][0] * L[b][0] + L[a][1] * L[b][1] + L[a][2] * L[b][2];
-            o.S[b][a] = o.S[a][b];
+            S[a][b] = L[a][0] * L[b][0] + L[a][1] * L[b][1] + L[a][2] * L[b][2];
+            S[b][a] = S[a][b];
         }
+}
+// cov3D_precomp layout of the replaced module: xx, xy, xz, yy, yz, zz
+__device__ __forceinline__ void load_sigma(const float* __restrict__ c, float (&S)[3][3]) {
+    S[0][0] = c[0]; S[0][1] = S[1][0] = c[1]; S[0][2] = S[2][0] = c[2];
+    S[1][1] = c[3]; S[1][2] = S[2][1] = c[4]; S[2][2] = c[5];
+}
+
+// Everything from the 3D covariance o.S (set by the caller) to (a, b, c) of the 2D covariance.  Returns false if culled by
+// the near plane.
+__device__ __forceinline__ bool project_with_sigma(const float* __restrict__ vp, float px, float py, float pz,
+                                                   float focal_x, float focal_y, Proj& o) {
+    const float* V = vp;
+    const float* PV = vp + 16;
+    o.tx = V[0] * px + V[4] * py + V[8] * pz + V[12];
+    o.ty = V[1] * px + V[5] * py + V[9] * pz + V[13];
+    o.tz = V[2] * px + V[6] * py + V[10] * pz + V[14];
+    if (o.tz <= 0.2f) return false;
+    o.hx = PV[0] * px + PV[4] * py + PV[8] * pz + PV[12];
+    o.hy = PV[1] * px + PV[5] * py + PV[9] * pz + PV[13];
+    o.hw = PV[3] * px + PV[7] * py + PV[11] * pz + PV[15];
+    o.p_w = 1.0f / (o.hw + 0.0000001f);
     const float limx = 1.3f * vp[DM4D_VIEW_TANFOVX], limy = 1.3f * vp[DM4D_VIEW_TANFOVY];
     const float txtz = o.tx / o.tz, tytz = o.ty / o.tz;
     o.xmul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
@@ -99,7 +109,6 @@ __device__ __forceinline__ bool project_gaussian(const float* __restrict__ vp, f
     o.c += 0.3f;
     return true;
 }
-
 
 // View parameters of a block: a block of consecutive (view, Gaussian) indices touches at most two views when
 // P >= blockDim, so both parameter rows are staged in shared memory once (the kernels read ~40 of the 48 floats per
@@ -143,6 +152,7 @@ PreArgs make_pre_args(const dm4d_raster_desc* d, const RasterLayout& L, int32_t*
     a.opacities = d->opacities; a.opacities_stride = d->opacities_stride;
     a.colors = d->colors; a.colors_stride = d->colors_stride;
     a.colors2 = d->colors2; a.colors2_stride = d->colors2_stride;
+    a.cov3D = d->cov3D; a.cov3D_stride = d->cov3D_stride;
     a.view_params = d->view_params;
     a.g_rec = L.g_rec; a.g_rect = L.g_rect; a.tile_count = L.tile_count; a.radii = radii;
     return a;

@@ -132,22 +132,27 @@ class RasterState:
 class _RasterizeBatch(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, opacities, scales, rotations, colors, colors2, view_params, H, W,
-                capacity, distinct_sets, state_out, workspace, plan=None):
+                capacity, distinct_sets, state_out, workspace, plan=None, cov3D=None):
         l = _lib.lib()
         dev = means3D.device
         if dev.type != "cuda":
             raise _lib.Dm4dError("dreammesh4d_b200 rasterizer needs CUDA tensors (there is no CPU path)")
         channels = 3 if colors2 is None else 6
         m, ms, s0 = _prep(means3D, 3, "means3D")
-        sc, ss, s1 = _prep(scales, 3, "scales")
-        ro, rs, s2 = _prep(rotations, 4, "rotations")
+        if cov3D is not None:          # cov3D_precomp of the replaced module: scales / rotations are not read
+            cv, cvs, s1 = _prep(cov3D, 6, "cov3D_precomp")
+            sc, ss, ro, rs, s2 = None, 0, None, 0, 1
+        else:
+            cv, cvs = None, 0
+            sc, ss, s1 = _prep(scales, 3, "scales")
+            ro, rs, s2 = _prep(rotations, 4, "rotations")
         op, os_, s3 = _prep(opacities.reshape(*opacities.shape[:-1], 1) if opacities.dim() >= 2 else opacities.reshape(-1, 1),
                             1, "opacities")
         co, cs, s4 = _prep(colors, 3, "colors_precomp")
         c2, c2s, s5 = (None, 0, 1) if colors2 is None else _prep(colors2, 3, "colors2")
         P = m.shape[-2]
-        for t, nm in ((sc, "scales"), (ro, "rotations"), (op, "opacities"), (co, "colors")):
-            if t.shape[-2] != P:
+        for t, nm in ((sc, "scales"), (ro, "rotations"), (op, "opacities"), (co, "colors"), (cv, "cov3D_precomp")):
+            if t is not None and t.shape[-2] != P:
                 raise ValueError(f"{nm} has {t.shape[-2]} rows, means3D has {P}")
         n_sets = max(s0, s1, s2, s3, s4, s5)
         for s in (s0, s1, s2, s3, s4, s5):
@@ -166,6 +171,7 @@ class _RasterizeBatch(torch.autograd.Function):
         d.opacities, d.opacities_stride = ptr(op), os_
         d.colors, d.colors_stride = ptr(co), cs
         d.colors2, d.colors2_stride = ptr(c2), c2s
+        d.cov3D, d.cov3D_stride = ptr(cv), cvs
         d.view_params = ptr(vp)
 
         def sizes(cap):
@@ -224,11 +230,13 @@ class _RasterizeBatch(torch.autograd.Function):
         # so the workspaces are released by reference counting, not by the cyclic GC)
         state = RasterState(d, [m, sc, ro, op, co, c2, vp, geom, bin_, img, alpha.detach(), color.detach(), depth.detach()], capacity)
         state.radii = radii
+        state.cov3D = cv
         state.alpha_version = (alpha._version, color._version, depth._version)   # the backward reads these very images
         ctx.state = state
         ctx.workspace = workspace
-        ctx.shapes = (means3D.shape, scales.shape, rotations.shape, opacities.shape, colors.shape,
-                      None if colors2 is None else colors2.shape)
+        ctx.shapes = (means3D.shape, None if scales is None else scales.shape, None if rotations is None else rotations.shape,
+                      opacities.shape, colors.shape, None if colors2 is None else colors2.shape,
+                      None if cov3D is None else cov3D.shape)
         ctx.has_means2D = means2D is not None
         ctx.mark_non_differentiable(radii)
         if state_out is not None:
@@ -266,8 +274,11 @@ class _RasterizeBatch(torch.autograd.Function):
         d_means3D = torch.empty_like(m) if need[0] else None
         d_means2D = torch.empty(d.n_views, d.P, 3, **f32) if (ctx.has_means2D and need[1]) else None
         d_opac = torch.empty_like(op) if need[2] else None
-        d_scales = torch.empty_like(sc) if need[3] else None
-        d_rots = torch.empty_like(ro) if need[4] else None
+        d_scales = torch.empty_like(sc) if (sc is not None and need[3]) else None
+        d_rots = torch.empty_like(ro) if (ro is not None and need[4]) else None
+        cv = getattr(st, "cov3D", None)
+        d_cov = torch.empty_like(cv) if (cv is not None and need[15]) else None
+        d.dL_dcov3D = ptr(d_cov)
         d_colors = torch.empty_like(co) if need[5] else None
         d_colors2 = torch.empty_like(c2) if (c2 is not None and need[6]) else None
         check(l.dm4d_raster_backward(ctypes.byref(d), ptr(color), ptr(depth), ptr(alpha), ptr(gC), ptr(gD), ptr(gA), ptr(d_means3D),
@@ -277,12 +288,12 @@ class _RasterizeBatch(torch.autograd.Function):
         rs = lambda t, s: None if t is None else t.reshape(s)
         return (rs(d_means3D, sh[0]), d_means2D, rs(d_opac, sh[3]), rs(d_scales, sh[1]), rs(d_rots, sh[2]),
                 rs(d_colors, sh[4]), None if d_colors2 is None else rs(d_colors2, sh[5]),
-                None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, rs(d_cov, sh[6]))
 
 
 def rasterize_batch(means3D, opacities, scales, rotations, colors, view_params, H, W, colors2=None, means2D=None,
                     capacity: Optional[int] = None, distinct_sets: bool = False, state_out: Optional[list] = None,
-                    workspace: Optional[RasterWorkspace] = None, plan: Optional[RasterState] = None):
+                    workspace: Optional[RasterWorkspace] = None, plan: Optional[RasterState] = None, cov3D=None):
     """Rasterizes a batch of views in one launch sequence.
 
     Attributes are ``[P,k]`` (shared by all views) or ``[S,P,k]`` (one set per timestamp; each view picks
@@ -294,10 +305,12 @@ def rasterize_batch(means3D, opacities, scales, rotations, colors, view_params, 
     (``RasterWorkspace``) for strictly alternating forward/backward call sequences.  ``plan``: the ``RasterState`` of an
     earlier call on the SAME means / scales / rotations / opacities / cameras — projection, binning and the depth sort
     are re-used and only ``colors`` (/``colors2``) are re-bound (the renderer's normal pass, temporal.py:202-211).
+    ``cov3D`` ([P,6] or [S,P,6]: xx, xy, xz, yy, yz, zz): precomputed 3D covariances instead of ``scales`` / ``rotations``
+    (``cov3D_precomp`` of the replaced module; the scale modifier does not apply).
     Returns ``color [B,C,H,W], radii [B,P] int32, depth [B,1,H,W], alpha [B,1,H,W]``.
     """
     return _RasterizeBatch.apply(means3D, means2D, opacities, scales, rotations, colors, colors2, view_params,
-                                 int(H), int(W), capacity, distinct_sets, state_out, workspace, plan)
+                                 int(H), int(W), capacity, distinct_sets, state_out, workspace, plan, cov3D)
 
 
 # --------------------------------------------------------------------------------------------
@@ -497,9 +510,6 @@ class GaussianRasterizer(nn.Module):
         if ((scales is None or rotations is None) and cov3D_precomp is None) or (
                 (scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
-        if cov3D_precomp is not None:
-            raise NotImplementedError("cov3D_precomp is not on the DreamMesh4D hot path "
-                                      "(the plugin always passes scales/rotations; DESIGN.md §2)")
         if shs is not None:
             # SH -> RGB as the replaced module does it in its preprocess (computeColorFromSH): evaluated here with device
             # tensor ops, then rasterized as precomputed colours.  Reached by the reference only in predict_step
@@ -508,6 +518,12 @@ class GaussianRasterizer(nn.Module):
         vp = self._view_params()
         m2d = None if means2D is None else means2D.reshape(1, -1, 3)
         H, W = int(rs.image_height), int(rs.image_width)
+        if cov3D_precomp is not None:
+            # precomputed 3D covariances (never passed by the DreamMesh4D plugin, which always hands over scales / rotations:
+            # diff_sugar_rasterizer_temporal.py:146-158): plain call, exact sizing, no plan re-use
+            color, radii, depth, alpha = rasterize_batch(means3D, opacities, None, None, colors_precomp, vp, H, W,
+                                                         means2D=m2d, cov3D=cov3D_precomp)
+            return color[0], radii[0], depth[0], alpha[0]
         plan = self._plan_hit(means3D, scales, rotations, opacities)
         st: list = []
         if plan is not None:

@@ -91,6 +91,12 @@ typedef struct dm4d_raster_desc {
     void* img;  uint64_t img_bytes;                     /* per-pixel n_contrib */
     void* bwd;  uint64_t bwd_bytes;                     /* backward accumulators (may be NULL for forward) */
     int64_t bin_capacity;                               /* instance capacity the bin workspace was sized for */
+    /* cov3D_precomp of the replaced module (optional): the 3D covariances [., P, 6] (xx, xy, xz, yy, yz, zz) instead of
+     * scales / rotations, which are then ignored and may be NULL; the scale modifier does not apply to them.  The backward
+     * writes dL_dcov3D (same shape, the gradient w.r.t. the six unique entries: off-diagonal terms counted twice, as the
+     * replaced rasterizer does) when the pointer is non-NULL. */
+    const float* cov3D;     int64_t cov3D_stride;
+    float* dL_dcov3D;
 } dm4d_raster_desc;
 
 /* Workspace sizes for a batch. `bin_capacity` = max number of (Gaussian, tile) instances. */

@@ -50,7 +50,9 @@ def test_argument_validation_matches_the_replaced_module():
         r(means3D=z(3), means2D=z(3), opacities=z(1), scales=z(3), rotations=z(4))
     with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
         r(means3D=z(3), means2D=z(3), opacities=z(1), colors_precomp=z(3))
-    with pytest.raises(NotImplementedError):
+    # cov3D_precomp is accepted (CUDA tensors only: there is no CPU path)
+    from dreammesh4d_b200._lib import Dm4dError
+    with pytest.raises(Dm4dError, match="CUDA"):
         r(means3D=z(3), means2D=z(3), opacities=z(1), colors_precomp=z(3), cov3D_precomp=torch.zeros(4, 6))
 
 

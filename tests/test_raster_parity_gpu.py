@@ -277,3 +277,46 @@ def test_tile_sort_tier_boundaries(P):
     color, radii, depth, alpha = R.rasterize_batch(d(means), d(opac), d(scales), d(rots), d(cols), vp, H, W, state_out=states)
     assert int((radii[0] > 0).sum()) == P                                  # nothing culled: the tile's segment has P keys
     check_view(o, color[0], radii[0], depth[0], alpha[0], states[0], 0, max_ambig=0.05)
+
+
+def test_cov3d_precomp_matches_scale_rotation_path():
+    """``cov3D_precomp=`` of the drop-in module: with Sigma = L L^T (L = R(q) diag(s)) evaluated in the kernel's own
+    operation order (separately rounded fp32), the integer state and the images are IDENTICAL to the scales / rotations
+    call (and hence to the oracle), and dL/dcov3D pulled back through Sigma(s, q) reproduces dL/dscales, dL/drotations."""
+    P, H, W = 4000, 96, 128
+    means, scales, rots, opac, cols = Hh.random_scene(P, 21)
+    V, PV, campos, tanx, tany = Hh.cameras(1, seed=31)
+    bg = torch.tensor([0.3, 0.2, 0.1])
+
+    def sigma(s, q):                      # the kernel's formula and order (raster_project.cuh: gaussian_sigma)
+        r, x, y, z = q.unbind(-1)
+        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                         2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                         2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=-1).reshape(-1, 3, 3)
+        L = R * s[:, None, :]
+        S = lambda a, b: L[:, a, 0] * L[:, b, 0] + L[:, a, 1] * L[:, b, 1] + L[:, a, 2] * L[:, b, 2]
+        return torch.stack([S(0, 0), S(0, 1), S(0, 2), S(1, 1), S(1, 2), S(2, 2)], dim=-1)
+
+    d = lambda x: x.to(DEV)
+    settings = R.GaussianRasterizationSettings(H, W, float(tanx[0]), float(tanx[0] * 0 + tany[0]), d(bg), 1.0, d(V[0]), d(PV[0]), 0,
+                                               d(campos[0]), False, False)
+    ts, tq = d(scales).requires_grad_(True), d(rots).requires_grad_(True)
+    tm, to_, tc = d(means).requires_grad_(True), d(opac), d(cols)
+    c1, r1, d1, a1 = R.GaussianRasterizer(settings)(means3D=tm, means2D=None, opacities=to_, colors_precomp=tc, scales=ts, rotations=tq)
+    cov = sigma(scales, rots)             # CPU fp32, op by op like the kernel (-fmad=false)
+    tcov = d(cov).requires_grad_(True)
+    tm2 = d(means).requires_grad_(True)
+    c2, r2, d2, a2 = R.GaussianRasterizer(settings)(means3D=tm2, means2D=None, opacities=to_, colors_precomp=tc, cov3D_precomp=tcov)
+    assert torch.equal(r1, r2)
+    for x, y in ((c1, c2), (d1, d2), (a1, a2)):
+        assert Hh.rel_linf(y.detach().cpu().numpy(), x.detach().cpu().numpy()) <= 1e-6
+    g = torch.Generator().manual_seed(5)
+    gC, gD, gA = d(torch.randn(3, H, W, generator=g)), d(torch.randn(1, H, W, generator=g)), d(torch.randn(1, H, W, generator=g))
+    ((c1 * gC).sum() + (d1 * gD).sum() + (a1 * gA).sum()).backward()
+    ((c2 * gC).sum() + (d2 * gD).sum() + (a2 * gA).sum()).backward()
+    assert Hh.rel_linf(tm2.grad.cpu().numpy(), tm.grad.cpu().numpy()) <= 1e-5
+    # pull dL/dcov3D back through Sigma(s, q) in fp64
+    s64, q64 = scales.double().requires_grad_(True), rots.double().requires_grad_(True)
+    (sigma(s64, q64) * tcov.grad.cpu().double()).sum().backward()
+    assert Hh.rel_linf(s64.grad.numpy(), ts.grad.cpu().double().numpy()) <= Hh.TOL_GRAD
+    assert Hh.rel_linf(q64.grad.numpy(), tq.grad.cpu().double().numpy()) <= Hh.TOL_GRAD
