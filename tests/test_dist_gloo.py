@@ -10,20 +10,19 @@ from dreammesh4d_b200 import dist as D
 
 
 def _worker(rank, world, port, ret):
+    """FlatGradBucket: every .grad is a view of one flat buffer; all_reduce sums it across ranks in one collective."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        n_frames, M = 6, 5
-        mine = D.shard_views(n_frames, rank, world)
-        g = torch.Generator().manual_seed(100)
-        all_t = torch.randn(n_frames, M, 3, generator=g)
-        all_r = torch.randn(n_frames, M, 4, generator=g)
-        out = D.node_gradient_exchange([all_t[mine] * (rank + 1), all_r[mine] * (rank + 1)], mine, n_frames)
-        scale = torch.tensor([float(1 + (f % world)) for f in range(n_frames)])[:, None, None]
-        ok = torch.allclose(out[0], all_t * scale) and torch.allclose(out[1], all_r * scale)
-        a, b = torch.full((3, 2), float(rank + 1)), torch.full((4,), float(10 * (rank + 1)))
-        D.allreduce_sum_([a, None, b])
-        ok = ok and torch.allclose(a, torch.full((3, 2), 3.0)) and torch.allclose(b, torch.full((4,), 30.0))
+        from dreammesh4d_b200.trainstep import FlatGradBucket
+        params = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(4)),
+                  torch.nn.Parameter(torch.zeros(5), requires_grad=False)]
+        bucket = FlatGradBucket(params)
+        params[0].grad.fill_(float(rank + 1))
+        params[1].grad.fill_(float(10 * (rank + 1)))
+        bucket.all_reduce()
+        ok = torch.allclose(params[0].grad, torch.full((3, 2), 3.0)) and torch.allclose(params[1].grad, torch.full((4,), 30.0))
+        ok = ok and params[0].grad.data_ptr() == bucket.flat.data_ptr() and params[2].grad is None
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
@@ -31,7 +30,7 @@ def _worker(rank, world, port, ret):
 
 def test_view_sharding_is_a_partition():
     for n, w in ((8, 1), (8, 2), (8, 8), (7, 4)):
-        parts = D.views_of_all_ranks(n, w)
+        parts = [D.shard_views(n, r, w) for r in range(w)]
         assert sorted(torch.cat(parts).tolist()) == list(range(n))
 
 
