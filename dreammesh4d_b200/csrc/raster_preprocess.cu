@@ -13,6 +13,7 @@ namespace {
 constexpr int SMEM_TILES = 4096;   // per-view tile histogram kept in shared memory (<= 1024x1024 px)
 
 // Projects one (view, Gaussian); returns the packed tile rect (0 = culled).
+template <bool COV>
 __device__ __forceinline__ unsigned int preprocess_one(const PreArgs& a, long long idx, int v, int g, const float* __restrict__ vp) {
     const long long set = min(max((long long)vp[DM4D_VIEW_SET], 0ll), (long long)a.n_sets - 1);   // never index outside the sets
 
@@ -24,7 +25,7 @@ __device__ __forceinline__ unsigned int preprocess_one(const PreArgs& a, long lo
     const float focal_y = (float)a.H / (2.0f * vp[DM4D_VIEW_TANFOVY]);
 
     Proj pr;
-    if (a.cov3D) {
+    if (COV) {
         load_sigma(a.cov3D + set * a.cov3D_stride + (size_t)g * 6, pr.S);
     } else {
         const float* sc = a.scales + set * a.scales_stride + (size_t)g * 3;
@@ -84,6 +85,7 @@ __device__ __forceinline__ unsigned int preprocess_one(const PreArgs& a, long lo
 // One thread per (view, Gaussian).  Instances per tile are counted in a per-block shared-memory histogram
 // (a block's 256 consecutive Gaussians are mesh-coherent and hit a few dozen tiles) and flushed with one
 // global atomic per touched tile; blocks that straddle two views or very large images count globally.
+template <bool COV>
 __global__ void __launch_bounds__(DM4D_BLOCK) preprocess_kernel(PreArgs a) {
     __shared__ unsigned int hist[SMEM_TILES];
     __shared__ ViewCache vcache;
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK) preprocess_kernel(PreArgs a) {
     __syncthreads();
     int v = 0, g = 0;
     if (idx < total) split_index(first, threadIdx.x, a.P, v, g);
-    const unsigned int rect = idx < total ? preprocess_one(a, idx, v, g, vc.row(v)) : 0u;
+    const unsigned int rect = idx < total ? preprocess_one<COV>(a, idx, v, g, vc.row(v)) : 0u;
     if (rect) {
         const int minx = rect & 0xff, miny = (rect >> 8) & 0xff, maxx = (rect >> 16) & 0xff, maxy = rect >> 24;
         if (use_smem) {
@@ -129,7 +131,11 @@ int launch_preprocess(const dm4d_raster_desc* d, const RasterLayout& L, int32_t*
     if (n == 0) return DM4D_OK;
     PreArgs a = make_pre_args(d, L, radii);
     const unsigned blocks = (unsigned)((n + DM4D_BLOCK - 1) / DM4D_BLOCK);
-    { KernelTimer kt(DM4D_K_PREPROCESS, s); preprocess_kernel<<<blocks, DM4D_BLOCK, 0, s>>>(a); }
+    {
+        KernelTimer kt(DM4D_K_PREPROCESS, s);
+        if (a.cov3D) preprocess_kernel<true><<<blocks, DM4D_BLOCK, 0, s>>>(a);
+        else preprocess_kernel<false><<<blocks, DM4D_BLOCK, 0, s>>>(a);
+    }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }

@@ -26,6 +26,7 @@ __device__ __forceinline__ void emit(float* p, float v, int atomic) {
 #ifndef DM4D_PREBWD_MIN_BLOCKS
 #define DM4D_PREBWD_MIN_BLOCKS 4
 #endif
+template <bool COV>
 __global__ void __launch_bounds__(DM4D_BLOCK, DM4D_PREBWD_MIN_BLOCKS) preprocess_backward_kernel(PreBwdArgs b) {
     __shared__ ViewCache vcache;
     ViewRows vc;
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK, DM4D_PREBWD_MIN_BLOCKS) preprocess
         const float px = m[0], py = m[1], pz = m[2];
         float q[4] = {1.f, 0.f, 0.f, 0.f}, s[3] = {0.f, 0.f, 0.f};
         Proj pr;
-        if (a.cov3D) {
+        if (COV) {
             load_sigma(a.cov3D + set * a.cov3D_stride + (size_t)g * 6, pr.S);
         } else {
             const float* sc = a.scales + set * a.scales_stride + (size_t)g * 3;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK, DM4D_PREBWD_MIN_BLOCKS) preprocess
             dm[k] += (V[2 + 4 * k] - V[3 + 4 * k] * pr.tz) * gd;
         }
 
-        if (a.cov3D) {
+        if (COV) {
             // gradient w.r.t. the six unique entries of the precomputed covariance (off-diagonal entries occur twice)
             dcov[0] = GS[0][0]; dcov[1] = 2.f * GS[0][1]; dcov[2] = 2.f * GS[0][2];
             dcov[3] = GS[1][1]; dcov[4] = 2.f * GS[1][2]; dcov[5] = GS[2][2];
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK, DM4D_PREBWD_MIN_BLOCKS) preprocess
         float* o = b.drots + set * a.rotations_stride + (size_t)g * 4;
         for (int k = 0; k < 4; ++k) emit(o + k, dq[k], b.drots_atomic);
     }
-    if (b.dcov && (live || !b.dcov_atomic)) {
+    if (COV && b.dcov && (live || !b.dcov_atomic)) {
         float* o = b.dcov + set * a.cov3D_stride + (size_t)g * 6;
         for (int k = 0; k < 6; ++k) emit(o + k, dcov[k], b.dcov_atomic);
     }
@@ -216,7 +217,11 @@ int launch_preprocess_backward(const dm4d_raster_desc* d, const RasterLayout& L,
     b.dcov = d->cov3D ? d->dL_dcov3D : nullptr; b.dcov_atomic = mode(b.dcov, d->cov3D_stride, P * 6);
     if (d->cov3D) { b.dscales = nullptr; b.drots = nullptr; }        // scales / rotations are not inputs of this call
     const unsigned blocks = (unsigned)((n + DM4D_BLOCK - 1) / DM4D_BLOCK);
-    { KernelTimer kt(DM4D_K_PREPROCESS_BWD, s); preprocess_backward_kernel<<<blocks, DM4D_BLOCK, 0, s>>>(b); }
+    {
+        KernelTimer kt(DM4D_K_PREPROCESS_BWD, s);
+        if (d->cov3D) preprocess_backward_kernel<true><<<blocks, DM4D_BLOCK, 0, s>>>(b);
+        else preprocess_backward_kernel<false><<<blocks, DM4D_BLOCK, 0, s>>>(b);
+    }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
 }
