@@ -55,8 +55,8 @@ static_assert(WARPS == 1 || WARPS == 2 || WARPS == 4 || WARPS == 8, "DM4D_RENDER
 #define DM4D_WSTAGES 2
 #endif
 #ifndef DM4D_BWD_MIN_WARPS
-#define DM4D_BWD_MIN_WARPS 32     // resident warps per SM the backward's register budget is sized for
-#endif
+#define DM4D_BWD_MIN_WARPS 24     // resident warps per SM the backward's register budget is sized for (measured at C3: no
+#endif                            // cap (90 registers) 0.841 ms, 20: 0.825, 24 (85 registers): 0.805, 28: 0.863, 32: 0.904)
 #define DM4D_BWD_MIN_BLOCKS (DM4D_BWD_MIN_WARPS / DM4D_RENDER_WARPS)
 constexpr int WCHUNK = DM4D_WCHUNK;     // instances per per-warp stage
 constexpr int WSTAGES = DM4D_WSTAGES;   // per-warp ring depth
@@ -362,7 +362,10 @@ __device__ __forceinline__ CellQueue cell_queue32(const float4* r, int cnt, int 
 // the per-pixel loss gradients of the warp's two cells, and the instance slot of every pair.
 template <int C>
 struct BwdScratch {
-    static constexpr int SLOTS = 16;               // pairs per half-warp per batch
+#ifndef DM4D_BWD_SLOTS
+#define DM4D_BWD_SLOTS 16
+#endif
+    static constexpr int SLOTS = DM4D_BWD_SLOTS;   // pairs per half-warp per batch
     static constexpr int ROW = 34;                 // floats per pair: 16 pixels x (h, w) + 2 pad -> conflict-free 8-byte accesses
     static constexpr int PC = C <= 3 ? 4 : 8;      // per-pixel constants: dL/dC[0..C), dL/dD (+ pad)
     float hw[2 * SLOTS * ROW];
@@ -375,7 +378,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 template <int C>
-__global__ void __launch_bounds__(THREADS) render_backward_kernel(RasterLayout L, const float* __restrict__ view_params,
+__global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_kernel(RasterLayout L, const float* __restrict__ view_params,
                                                                    const float* __restrict__ out_color,
                                                                    const float* __restrict__ out_depth,
                                                                    const float* __restrict__ out_alpha,
