@@ -411,8 +411,14 @@ __device__ __forceinline__ void pack_tile(const unsigned long long* keys, int n,
 // instances, C4's densest ~10^4).  Small CTAs keep more tiles resident per SM and their pass barriers span 4 warps.
 // Only segments above 16384 keys fall back to chunked bitonic merging through global memory — that path took 0.25 ms for
 // a 6000-key tile and was the whole tail of the launch when the largest in-memory tier was 4096.
+#ifndef DM4D_SORT_M_BLOCKS
+#define DM4D_SORT_M_BLOCKS 3      // resident CTAs per SM the 512-thread tier's register budget is sized for
+#endif
+#ifndef DM4D_SORT_S_BLOCKS
+#define DM4D_SORT_S_BLOCKS 10     // ... and the 128-thread tier's
+#endif
 template <int THREADS, int E, int R4>
-__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : (THREADS == 512 ? 3 : 10)) sort_pack_kernel(RasterLayout L, int n_lo, int n_hi) {
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : (THREADS == 512 ? DM4D_SORT_M_BLOCKS : DM4D_SORT_S_BLOCKS)) sort_pack_kernel(RasterLayout L, int n_lo, int n_hi) {
     constexpr int SORT_CHUNK = THREADS * E;
     extern __shared__ __align__(16) unsigned long long sk[];   // [SORT_CHUNK]
     if (L.hdr->overflow) return;

@@ -85,8 +85,11 @@ __device__ __forceinline__ unsigned int preprocess_one(const PreArgs& a, long lo
 // One thread per (view, Gaussian).  Instances per tile are counted in a per-block shared-memory histogram
 // (a block's 256 consecutive Gaussians are mesh-coherent and hit a few dozen tiles) and flushed with one
 // global atomic per touched tile; blocks that straddle two views or very large images count globally.
+#ifndef DM4D_PRE_MIN_BLOCKS
+#define DM4D_PRE_MIN_BLOCKS 4
+#endif
 template <bool COV>
-__global__ void __launch_bounds__(DM4D_BLOCK) preprocess_kernel(PreArgs a) {
+__global__ void __launch_bounds__(DM4D_BLOCK, DM4D_PRE_MIN_BLOCKS) preprocess_kernel(PreArgs a) {
     __shared__ unsigned int hist[SMEM_TILES];
     __shared__ ViewCache vcache;
     ViewRows vc;
