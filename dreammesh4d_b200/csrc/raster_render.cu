@@ -378,7 +378,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 template <int C>
-__global__ void __launch_bounds__(THREADS, DM4D_BWD_MIN_BLOCKS) render_backward_kernel(RasterLayout L, const float* __restrict__ view_params,
+// the 6-channel instantiation needs 96 registers: its budget stays at 20 warps per SM (no spills)
+__global__ void __launch_bounds__(THREADS, C <= 3 ? DM4D_BWD_MIN_BLOCKS : (20 / DM4D_RENDER_WARPS)) render_backward_kernel(RasterLayout L, const float* __restrict__ view_params,
                                                                    const float* __restrict__ out_color,
                                                                    const float* __restrict__ out_depth,
                                                                    const float* __restrict__ out_alpha,
