@@ -16,6 +16,17 @@
 #include <algorithm>
 #include "raster_internal.cuh"
 
+// register budgets (resident CTAs per SM) of the kernels whose occupancy is register-bound; tuning: scripts/tune_c5.sh
+#ifndef DM4D_SKIN_GF_BLOCKS
+#define DM4D_SKIN_GF_BLOCKS 4      // measured at C5 x 8 timestamps (us): unbounded 114, 3: 114, 4: 103
+#endif
+#ifndef DM4D_SKIN_GB_BLOCKS
+#define DM4D_SKIN_GB_BLOCKS 4      // 2: 237, 3: 196, 4: 187
+#endif
+#ifndef DM4D_SKIN_NB_BLOCKS
+#define DM4D_SKIN_NB_BLOCKS 4      // vertex backward (upstream + node kernels): unbounded 222, 3: 222, 4: 210
+#endif
+
 namespace {
 
 constexpr float EPS_LIE = 1e-6f;
@@ -368,7 +379,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK) skin_vertex_upstream_kernel(SkinBw
     o[3] = u.dsq_d;
 }
 
-__global__ void __launch_bounds__(DM4D_BLOCK) skin_node_backward_kernel(SkinBwdK a, const float4* __restrict__ up,
+__global__ void __launch_bounds__(DM4D_BLOCK, DM4D_SKIN_NB_BLOCKS) skin_node_backward_kernel(SkinBwdK a, const float4* __restrict__ up,
                                                                         const int32_t* __restrict__ inc_ptr,
                                                                         const int32_t* __restrict__ inc) {
     __shared__ float part[DM4D_BLOCK / 32][17];
@@ -588,7 +599,7 @@ __device__ __forceinline__ void warp_load_block(float* st, const float* __restri
     }
 }
 
-__global__ void __launch_bounds__(DM4D_BLOCK) skin_gaussian_forward_kernel(SkinK a) {
+__global__ void __launch_bounds__(DM4D_BLOCK, DM4D_SKIN_GF_BLOCKS) skin_gaussian_forward_kernel(SkinK a) {
     __shared__ __align__(16) float stage_all[DM4D_BLOCK / 32][STAGE_FLOATS];
     const dm4d_skin_desc& d = a.d;
     const int lane = threadIdx.x & 31, g = d.g;
@@ -661,7 +672,7 @@ __global__ void __launch_bounds__(DM4D_BLOCK) skin_gaussian_forward_kernel(SkinK
     }
 }
 
-__global__ void __launch_bounds__(DM4D_BLOCK, 3) skin_gaussian_backward_kernel(SkinBwdK a) {
+__global__ void __launch_bounds__(DM4D_BLOCK, DM4D_SKIN_GB_BLOCKS) skin_gaussian_backward_kernel(SkinBwdK a) {
     __shared__ __align__(16) float stage_all[DM4D_BLOCK / 32][STAGE_FLOATS];
     const dm4d_skin_desc& d = a.d;
     const int lane = threadIdx.x & 31, g = d.g;
