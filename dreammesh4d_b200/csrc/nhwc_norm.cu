@@ -8,17 +8,14 @@
 //   y[n,p,c] = act( ((x[n,p,c] + e[n,c]) - mean[n,g]) * rstd[n,g] * gamma[c] + beta[c] ),   g = c / (C / G)
 //
 // Layout: x, y are [N, HW, C] (the memory of a torch channels_last [N,C,H,W] tensor), fp16 or fp32; statistics in fp32.
-// ONE persistent launch each way.  Work items = (sample, pixel slab) x {statistics, apply}, handed out in order by an
-// atomic counter: the statistics items of sample n run a bounded distance (~24 MB of activations) ahead of its apply
-// items, so the apply pass finds the sample in the 126 MB L2 instead of re-reading HBM, and an apply item only waits
-// (on a per-sample arrival counter) for items that were fetched before it — deadlock-free without co-residency.
-// The encoder's 134 MB activations cost 3 HBM passes instead of 3 + 1 (forward) and 3 instead of 5 (backward); the
-// UNet's small ones one launch instead of three.
+// Two streamed launches each way (statistics, apply) with 16-byte accesses, or — for the UNet's small fp16 activations —
+// one launch that keeps its slab in registers between the two phases.
 // Backward (weights are frozen in the SDS step: no dgamma / dbeta) needs the two group sums of dz*gamma and dz*gamma*xhat.
 #include <algorithm>
 #include <cmath>
 #include <cuda_fp16.h>
 #include "raster_internal.cuh"
+
 
 namespace {
 
@@ -70,9 +67,16 @@ struct NormArgs {
     int silu;
 };
 
-__device__ __forceinline__ float silu_f(float z) { return z / (1.0f + __expf(-z)); }
+// sigmoid through MUFU.EX2 + MUFU.RCP (1-2 ulp): the IEEE division cost ~10 instructions per element and made the
+// backward passes instruction-bound (two evaluations per element and pass)
+__device__ __forceinline__ float approx_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float silu_f(float z) { return z * approx_rcp(1.0f + __expf(-z)); }
 __device__ __forceinline__ float silu_grad(float z) {
-    const float s = 1.0f / (1.0f + __expf(-z));
+    const float s = approx_rcp(1.0f + __expf(-z));
     return s * (1.0f + z * (1.0f - s));
 }
 
@@ -82,147 +86,167 @@ __device__ __forceinline__ float silu_grad(float z) {
 // Backward: dx = rstd * (dz*gamma - mean_g(dz*gamma) - xhat * mean_g(dz*gamma*xhat)),  dz = dy * act'(z)
 // (d chan_bias is not produced: the time embedding carries no gradient in the SDS step).
 
-// ---- single-launch persistent GroupNorm ------------------------------------------------------------------------------
-struct FusedArgs {
-    NormArgs a;
-    int slabs;            // pixel slabs per sample
-    int ahead;            // statistics run this many samples ahead of the apply pass
+// ---- streamed GroupNorm (every activation that does not take the register-resident path below) ------------------------
+// Two launches each way over (sample, pixel slab) blocks with 16-byte accesses and four pixels in flight per thread:
+//   statistics: per-channel partial sums in registers -> group bins in shared memory -> one global atomic per (block, group,
+//               moment);   apply: the element-wise pass, group statistics finalised inline.
+// A single persistent launch with an ordered work queue (statistics a bounded distance ahead of the apply pass so that the
+// second read hits L2) was measured first: ncu showed the re-read still coming from DRAM (499 of 536 MB in the backward of
+// an [8,128,256,256] activation) and the per-item synchronisation costing more than the saved launches — 157 / 353 us
+// forward / backward against a 41 / 62 us HBM bound.
+struct SumsArgs {
     float* sums;          // [N,G,2] zeroed: forward (sum, sum sq) / backward (sum dz*gamma, sum dz*gamma*xhat)
-    int* counters;        // [1 + N] zeroed: work counter, per-sample arrivals of statistics items
+};
+struct FusedArgs {        // arguments of the register-resident kernel
+    NormArgs a;
+    int slabs;
+    int ahead;
+    float* sums;
+    int* counters;        // [1 + N] zeroed: (unused), per-sample arrivals
 };
 
-// group g of the item order  S(0..D-1), A(0), S(D), A(1), S(D+1), ..., A(N-D..N-1)
-__device__ __forceinline__ void decode_group(int g, int N, int D, bool& apply, int& n) {
-    if (g < D) { apply = false; n = g; }
-    else if (g < 2 * N - D) { const int r = g - D; apply = (r & 1) == 0; n = apply ? r / 2 : r / 2 + D; }
-    else { apply = true; n = g - N; }
+template <typename T> struct Wide;       // 16-byte accesses: 4 fp32 / 8 fp16 channels
+template <> struct Wide<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) { Vec4<float>::load(p, v); }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { Vec4<float>::store(p, v); }
+};
+template <> struct Wide<__half> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p);
+        const unsigned int w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+    static __device__ __forceinline__ void store(__half* p, const float (&v)[8]) {
+        unsigned int w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<__half2*>(&w[i]) = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+template <typename T, int VW> struct IO;
+template <typename T> struct IO<T, 4> : Vec4<T> {};
+template <> struct IO<__half, 8> : Wide<__half> {};
+
+// a.cvec = C / VW here.  grid = (slabs, N); thread (cv, r) owns channels [cv*VW, cv*VW+VW) and walks the pixels
+// p0 + r, p0 + r + k, ... of its slab.
+template <typename T, bool BWD, int VW>
+__global__ void __launch_bounds__(VW == 8 ? 512 : 1024) gn_stream_stats_kernel(NormArgs a, const T* __restrict__ x, const float* __restrict__ chan_bias,
+                                                               const T* __restrict__ dy, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, const float* __restrict__ stats,
+                                                               float* __restrict__ sums) {
+    __shared__ float bins[2 * MAX_GROUPS];
+    const int n = blockIdx.y;
+    const int cv = threadIdx.x % a.cvec, r = threadIdx.x / a.cvec, k = blockDim.x / a.cvec;
+    const int c0 = cv * VW;
+    for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) bins[i] = 0.f;
+    __syncthreads();
+    const int p0 = blockIdx.x * a.rows_per_block, p1 = min(a.HW, p0 + a.rows_per_block);
+    float s0[VW], s1[VW], e[VW], gam[VW], bet[VW], mu[VW], rs[VW];
+#pragma unroll
+    for (int j = 0; j < VW; ++j) {
+        s0[j] = s1[j] = 0.f;
+        e[j] = chan_bias ? chan_bias[(size_t)n * a.C + c0 + j] : 0.f;
+        if (BWD) {
+            const size_t sg = ((size_t)n * a.G + (c0 + j) / a.cpg) * 2;
+            gam[j] = gamma[c0 + j]; bet[j] = beta[c0 + j];
+            mu[j] = stats[sg]; rs[j] = stats[sg + 1];
+        }
+    }
+    const T* xn = x + (size_t)n * a.HW * a.C + c0;
+    const T* dn = BWD ? dy + (size_t)n * a.HW * a.C + c0 : nullptr;
+#pragma unroll 4
+    for (int p = p0 + r; p < p1; p += k) {
+        float v[VW];
+        IO<T, VW>::load(xn + (size_t)p * a.C, v);
+        if (!BWD) {
+#pragma unroll
+            for (int j = 0; j < VW; ++j) { const float t = v[j] + e[j]; s0[j] += t; s1[j] += t * t; }
+        } else {
+            float d[VW];
+            IO<T, VW>::load(dn + (size_t)p * a.C, d);
+#pragma unroll
+            for (int j = 0; j < VW; ++j) {
+                const float xh = (v[j] + e[j] - mu[j]) * rs[j];
+                float dz = d[j];
+                if (a.silu) dz *= silu_grad(xh * gam[j] + bet[j]);
+                const float t = dz * gam[j];
+                s0[j] += t; s1[j] += t * xh;
+            }
+        }
+    }
+    // channels of one thread that share a group are summed in registers before they touch the bins
+#pragma unroll
+    for (int j = 0; j < VW; ++j) {
+        const int g = (c0 + j) / a.cpg;
+        if (j + 1 < VW && (c0 + j + 1) / a.cpg == g) { s0[j + 1] += s0[j]; s1[j + 1] += s1[j]; continue; }
+        atomicAdd(&bins[2 * g], s0[j]);
+        atomicAdd(&bins[2 * g + 1], s1[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) atomicAdd(&sums[(size_t)n * 2 * a.G + i], bins[i]);
 }
 
-template <typename T, bool BWD>
-__global__ void gn_fused_kernel(FusedArgs f, const T* __restrict__ x, const float* __restrict__ chan_bias,
-                                const T* __restrict__ dy, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                float* __restrict__ stats /* fwd: out, bwd: in */, T* __restrict__ out) {
-    __shared__ float bins[2 * MAX_GROUPS];
-    __shared__ int s_item;
-    const NormArgs& a = f.a;
+template <typename T, bool BWD, int VW>
+__global__ void __launch_bounds__(VW == 8 ? 512 : 1024) gn_stream_apply_kernel(NormArgs a, const T* __restrict__ x, const float* __restrict__ chan_bias,
+                                                               const T* __restrict__ dy, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float* __restrict__ stats,
+                                                               const float* __restrict__ sums, T* __restrict__ out) {
+    const int n = blockIdx.y;
     const int cv = threadIdx.x % a.cvec, r = threadIdx.x / a.cvec, k = blockDim.x / a.cvec;
-    const int c0 = cv * VEC;
-    const int total = 2 * a.N * f.slabs;
-    const float count = (float)a.HW * (float)a.cpg, inv_count = 1.0f / count;
-    float gam[VEC], bet[VEC];
+    const int c0 = cv * VW;
+    const int p0 = blockIdx.x * a.rows_per_block, p1 = min(a.HW, p0 + a.rows_per_block);
+    const float inv_count = 1.0f / ((float)a.HW * (float)a.cpg);
+    // forward: y = act(v * sc + sh);  backward: dx = rs * (dz * gam - b0 - xh * b1), xh = v * rs + xo
+    float sc[VW], sh[VW], gam[VW], bet[VW], rs[VW], xo[VW], b0[VW], b1[VW];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) { gam[j] = gamma[c0 + j]; bet[j] = beta[c0 + j]; }
-    // first item = blockIdx.x (the grid never exceeds the resident capacity, so statically assigned items cannot be
-    // stuck behind spinning CTAs), later ones from the counter: one same-address atomic per EXTRA item only
-    for (int item = blockIdx.x; item < total;) {
-        bool apply; int n;
-        decode_group(item / f.slabs, a.N, f.ahead, apply, n);
-        const int slab = item % f.slabs;
-        const int p0 = slab * a.rows_per_block, p1 = min(a.HW, p0 + a.rows_per_block);
-        float e[VEC], mu[VEC], rs[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) e[j] = chan_bias ? chan_bias[(size_t)n * a.C + c0 + j] : 0.f;
-        if (apply || BWD) {
-            if (apply) {                               // all statistics items of sample n have arrived?
-                if (threadIdx.x == 0) {
-                    while (atomicAdd(&f.counters[1 + n], 0) < f.slabs) __nanosleep(64);
-                    __threadfence();
-                }
-                __syncthreads();
-            }
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const size_t sg = ((size_t)n * a.G + (c0 + j) / a.cpg) * 2;
-                if (BWD) { mu[j] = stats[sg]; rs[j] = stats[sg + 1]; }
-                else {
-                    const float mean = __ldcg(&f.sums[sg]) * inv_count;
-                    mu[j] = mean;
-                    rs[j] = rsqrtf(fmaxf(__ldcg(&f.sums[sg + 1]) * inv_count - mean * mean, 0.f) + a.eps);
-                }
-            }
-        }
-        if (!apply) {
-            for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) bins[i] = 0.f;
-            __syncthreads();
-            float s0[VEC], s1[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) s0[j] = s1[j] = 0.f;
-            for (int p = p0 + r; p < p1; p += k) {
-                const size_t off = ((size_t)n * a.HW + p) * a.C + c0;
-                float v[VEC];
-                Vec4<T>::load(x + off, v);
-                if (!BWD) {
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) { const float t = v[j] + e[j]; s0[j] += t; s1[j] += t * t; }
-                } else {
-                    float d[VEC];
-                    Vec4<T>::load(dy + off, d);
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        const float xh = (v[j] + e[j] - mu[j]) * rs[j];
-                        float dz = d[j];
-                        if (a.silu) dz *= silu_grad(xh * gam[j] + bet[j]);
-                        const float t = dz * gam[j];
-                        s0[j] += t; s1[j] += t * xh;
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const int g = (c0 + j) / a.cpg;
-                atomicAdd(&bins[2 * g], s0[j]);
-                atomicAdd(&bins[2 * g + 1], s1[j]);
-            }
-            __syncthreads();
-            for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) atomicAdd(&f.sums[(size_t)n * 2 * a.G + i], bins[i]);
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) atomicAdd(&f.counters[1 + n], 1);
+    for (int j = 0; j < VW; ++j) {
+        const size_t sg = ((size_t)n * a.G + (c0 + j) / a.cpg) * 2;
+        const float e = chan_bias ? chan_bias[(size_t)n * a.C + c0 + j] : 0.f;
+        gam[j] = gamma[c0 + j]; bet[j] = beta[c0 + j];
+        if (!BWD) {
+            const float mean = sums[sg] * inv_count;
+            const float rstd = rsqrtf(fmaxf(sums[sg + 1] * inv_count - mean * mean, 0.f) + a.eps);
+            if (blockIdx.x == 0 && r == 0 && (c0 + j) % a.cpg == 0) { stats[sg] = mean; stats[sg + 1] = rstd; }
+            sc[j] = rstd * gam[j];
+            sh[j] = (e - mean) * sc[j] + bet[j];
         } else {
-            float b0[VEC], b1[VEC];
-            if (BWD) {
+            rs[j] = stats[sg + 1];
+            xo[j] = (e - stats[sg]) * rs[j];
+            b0[j] = sums[sg] * inv_count; b1[j] = sums[sg + 1] * inv_count;
+        }
+    }
+    const T* xn = x + (size_t)n * a.HW * a.C + c0;
+    const T* dn = BWD ? dy + (size_t)n * a.HW * a.C + c0 : nullptr;
+    T* on = out + (size_t)n * a.HW * a.C + c0;
+#pragma unroll 4
+    for (int p = p0 + r; p < p1; p += k) {
+        float v[VW], o[VW];
+        IO<T, VW>::load(xn + (size_t)p * a.C, v);
+        if (!BWD) {
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    const size_t sg = ((size_t)n * a.G + (c0 + j) / a.cpg) * 2;
-                    b0[j] = __ldcg(&f.sums[sg]) * inv_count; b1[j] = __ldcg(&f.sums[sg + 1]) * inv_count;
-                }
-            } else if (slab == 0 && r == 0) {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    if ((c0 + j) % a.cpg == 0) {
-                        const size_t sg = ((size_t)n * a.G + (c0 + j) / a.cpg) * 2;
-                        stats[sg] = mu[j]; stats[sg + 1] = rs[j];
-                    }
-                }
+            for (int j = 0; j < VW; ++j) {
+                const float z = v[j] * sc[j] + sh[j];
+                o[j] = a.silu ? silu_f(z) : z;
             }
-            for (int p = p0 + r; p < p1; p += k) {
-                const size_t off = ((size_t)n * a.HW + p) * a.C + c0;
-                float v[VEC], o[VEC];
-                Vec4<T>::load(x + off, v);
-                if (!BWD) {
+        } else {
+            float d[VW];
+            IO<T, VW>::load(dn + (size_t)p * a.C, d);
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        const float z = (v[j] + e[j] - mu[j]) * rs[j] * gam[j] + bet[j];
-                        o[j] = a.silu ? silu_f(z) : z;
-                    }
-                } else {
-                    float d[VEC];
-                    Vec4<T>::load(dy + off, d);
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        const float xh = (v[j] + e[j] - mu[j]) * rs[j];
-                        float dz = d[j];
-                        if (a.silu) dz *= silu_grad(xh * gam[j] + bet[j]);
-                        o[j] = rs[j] * (dz * gam[j] - b0[j] - xh * b1[j]);
-                    }
-                }
-                Vec4<T>::store(out + off, o);
+            for (int j = 0; j < VW; ++j) {
+                const float xh = v[j] * rs[j] + xo[j];
+                float dz = d[j];
+                if (a.silu) dz *= silu_grad(xh * gam[j] + bet[j]);
+                o[j] = rs[j] * (dz * gam[j] - b0[j] - xh * b1[j]);
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) s_item = (int)gridDim.x + atomicAdd(&f.counters[0], 1);
-        __syncthreads();
-        item = s_item;
+        IO<T, VW>::store(on + (size_t)p * a.C, o);
     }
 }
 
@@ -317,25 +341,30 @@ int make_args(int N, int HW, int C, int G, float eps, int silu, NormArgs* a, int
     return DM4D_OK;
 }
 
+#ifndef DM4D_GN_FWD_VW
+#define DM4D_GN_FWD_VW 8      // fp16 channels per access in the forward kernels
+#endif
+#ifndef DM4D_GN_BWD_VW
+#define DM4D_GN_BWD_VW 4      // fp16 channels per access in the backward kernels (8: 16-byte accesses but ~100 registers)
+#endif
 template <typename T, bool BWD>
-int launch_fused(const NormArgs& a, int threads, dim3 grid, const void* x, const float* cb, const void* dy, const float* gamma,
-                 const float* beta, float* stats, float* scratch, void* out, cudaStream_t s) {
-    FusedArgs f;
-    f.a = a;
-    f.slabs = (int)grid.x;
-    // statistics lead the apply pass by ~24 MB of activations (x, and dy in the backward): well inside the L2
-    const double sample_bytes = (double)a.HW * a.C * sizeof(T) * (BWD ? 2 : 1);
-    f.ahead = (int)std::max(1.0, std::min((double)a.N, std::ceil(24e6 / sample_bytes)));
-    f.sums = scratch;
-    f.counters = reinterpret_cast<int*>(scratch + (size_t)a.N * a.G * 2);
-    DM4D_CUDA_CHECK(cudaMemsetAsync(scratch, 0, ((size_t)a.N * a.G * 2 + a.N + 1) * sizeof(float), s));
-    const int total = 2 * a.N * f.slabs;
-    int per_sm = 0;
-    DM4D_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel<T, BWD>, threads, 0));
-    const unsigned blocks = (unsigned)std::min(total, sm_count() * std::max(1, per_sm));
+int launch_stream(const NormArgs& a4, const void* x, const float* cb, const void* dy, const float* gamma, const float* beta,
+                  float* stats, float* scratch, void* out, cudaStream_t s) {
+    constexpr int VW = sizeof(T) == 2 ? (BWD ? DM4D_GN_BWD_VW : DM4D_GN_FWD_VW) : 4;
+    NormArgs a = a4;
+    if (a.C % VW) { dm4d_set_error("groupnorm_nhwc: C must be a multiple of %d for this dtype (C=%d)", VW, a.C); return DM4D_EINVAL; }
+    a.cvec = a.C / VW;
+    const int k = std::max(1, std::min(256 / a.cvec, a.HW));
+    const int threads = a.cvec * k;
+    // enough blocks per sample to fill the machine (SMs x a few CTAs), at least 8 pixels per thread row
+    const int slabs = std::max(1, std::min((a.HW + 8 * k - 1) / (8 * k), std::max(1, (sm_count() * 8 + a.N - 1) / a.N)));
+    a.rows_per_block = (a.HW + slabs - 1) / slabs;
+    const dim3 grid((unsigned)((a.HW + a.rows_per_block - 1) / a.rows_per_block), (unsigned)a.N);
+    DM4D_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)a.N * a.G * 2 * sizeof(float), s));
     {
         KernelTimer kt(BWD ? DM4D_K_GROUPNORM_BWD : DM4D_K_GROUPNORM_FWD, s);
-        gn_fused_kernel<T, BWD><<<blocks, threads, 0, s>>>(f, (const T*)x, cb, (const T*)dy, gamma, beta, stats, (T*)out);
+        gn_stream_stats_kernel<T, BWD, VW><<<grid, threads, 0, s>>>(a, (const T*)x, cb, (const T*)dy, gamma, beta, stats, scratch);
+        gn_stream_apply_kernel<T, BWD, VW><<<grid, threads, 0, s>>>(a, (const T*)x, cb, (const T*)dy, gamma, beta, stats, scratch, (T*)out);
     }
     DM4D_CUDA_CHECK(cudaGetLastError());
     return DM4D_OK;
@@ -370,13 +399,13 @@ int forward_t(const NormArgs& a, int threads, dim3 grid, const void* x, const fl
             return DM4D_OK;
         }
     }
-    return launch_fused<T, false>(a, threads, grid, x, cb, nullptr, gamma, beta, stats, scratch, y, s);
+    return launch_stream<T, false>(a, x, cb, nullptr, gamma, beta, stats, scratch, y, s);
 }
 
 template <typename T>
 int backward_t(const NormArgs& a, int threads, dim3 grid, const void* x, const float* cb, const void* dy, const float* gamma,
                const float* beta, const float* stats, float* scratch, void* dx, cudaStream_t s) {
-    return launch_fused<T, true>(a, threads, grid, x, cb, dy, gamma, beta, const_cast<float*>(stats), scratch, dx, s);
+    return launch_stream<T, true>(a, x, cb, dy, gamma, beta, const_cast<float*>(stats), scratch, dx, s);
 }
 
 // ---- convolution epilogues the library calls do not fuse ------------------------------------------------------------
