@@ -79,7 +79,7 @@ class GroupNormAct(nn.GroupNorm):
 
     def forward(self, x: torch.Tensor, chan_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
         if x.is_cuda and x.dtype in _DTYPES and not (self.weight.requires_grad or self.bias.requires_grad) and \
-                self.num_channels % (8 if x.dtype == torch.float16 else 4) == 0 and self.num_groups <= 64:
+                self.num_channels % 4 == 0 and self.num_groups <= 64:
             g32, b32 = self._params32()
             return groupnorm_nhwc(x, g32, b32, self.num_groups, self.eps, self.silu, chan_bias)
         if chan_bias is not None:

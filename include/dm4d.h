@@ -337,8 +337,8 @@ int dm4d_graph_geodesic_sweep(int32_t V, int32_t k, const int32_t* row_ptr, cons
  *     y[n,p,c] = act(((x[n,p,c] + chan_bias[n,c]) - mean[n,g]) * rstd[n,g] * gamma[c] + beta[c]),  g = c / (C/G)
  * x, y: [N, HW, C] = the memory of a torch channels_last [N,C,H,W] tensor, `dtype` DM4D_F16 or DM4D_F32.
  * chan_bias [N,C] fp32 or NULL; gamma, beta [C] fp32; stats [N,G,2] fp32 (mean, rstd; output of the forward, input of
- * the backward); scratch [N*G*2 + N + 1] 4-byte words (group sums + per-sample arrival counters).  C % G == 0, C % 4 == 0
- * (fp16: C % 8 == 0: 16-byte accesses), C <= 4096, G <= 64.  Two streamed launches per call (statistics, apply), or one
+ * the backward); scratch [N*G*2 + N + 1] 4-byte words (group sums + per-sample arrival counters).  C % G == 0, C % 4 == 0,
+ * C <= 4096, G <= 64.  Two streamed launches per call (statistics, apply), or one
  * register-resident launch for small fp16 activations. */
 #define DM4D_F32 0
 #define DM4D_F16 1
