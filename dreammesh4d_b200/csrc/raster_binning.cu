@@ -406,8 +406,8 @@ __device__ __forceinline__ void pack_tile(const unsigned long long* keys, int n,
     }
 }
 
-// Three CTA shapes share the tiles by segment length, all sorting in shared memory: 128 threads x 8 keys up to 1024
-// keys, 512 x 8 up to 4096, 1024 x 16 up to 16384 (128 KB of shared memory; the limb / centre tiles of C3 hold ~6000
+// Several CTA shapes share the tiles by segment length, all sorting in shared memory: 128 threads x 8 keys up to 1024
+// keys, 256 x 8 up to 2048, 512 x 8 up to 4096, 1024 x 8 up to 8192, 1024 x 16 up to 16384 (128 KB of shared memory; the limb / centre tiles of C3 hold ~6000
 // instances, C4's densest ~10^4).  Small CTAs keep more tiles resident per SM and their pass barriers span 4 warps.
 // Only segments above 16384 keys fall back to chunked bitonic merging through global memory — that path took 0.25 ms for
 // a 6000-key tile and was the whole tail of the launch when the largest in-memory tier was 4096.
@@ -417,8 +417,27 @@ __device__ __forceinline__ void pack_tile(const unsigned long long* keys, int n,
 #ifndef DM4D_SORT_S_BLOCKS
 #define DM4D_SORT_S_BLOCKS 10     // ... and the 128-thread tier's
 #endif
+// Finer tiers: a 256 x 8 tier for 1025..2048 keys (the 512-thread CTAs ran such a tile with half of their threads idle
+// and 16-warp barriers; on by default: -2 % step time at C4, neutral at C3) and an optional 64 x 8 tier for tiles of at
+// most 512 keys (no gain measured, off; profiles/r2aa_tune_sort_tiers.txt).
+#ifndef DM4D_SORT_TIER256
+#define DM4D_SORT_TIER256 1
+#endif
+#ifndef DM4D_SORT_TIER64
+#define DM4D_SORT_TIER64 0
+#endif
+#ifndef DM4D_SORT_H_BLOCKS
+#define DM4D_SORT_H_BLOCKS 6      // resident CTAs per SM the 256-thread tier's register budget is sized for
+#endif
+#ifndef DM4D_SORT_T_BLOCKS
+#define DM4D_SORT_T_BLOCKS 16     // ... and the 64-thread tier's
+#endif
+constexpr int sort_min_blocks(int threads) {
+    return threads == 1024 ? 1 : threads == 512 ? DM4D_SORT_M_BLOCKS : threads == 256 ? DM4D_SORT_H_BLOCKS
+         : threads == 128 ? DM4D_SORT_S_BLOCKS : DM4D_SORT_T_BLOCKS;
+}
 template <int THREADS, int E, int R4>
-__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : (THREADS == 512 ? DM4D_SORT_M_BLOCKS : DM4D_SORT_S_BLOCKS)) sort_pack_kernel(RasterLayout L, int n_lo, int n_hi) {
+__global__ void __launch_bounds__(THREADS, sort_min_blocks(THREADS)) sort_pack_kernel(RasterLayout L, int n_lo, int n_hi) {
     constexpr int SORT_CHUNK = THREADS * E;
     extern __shared__ __align__(16) unsigned long long sk[];   // [SORT_CHUNK]
     if (L.hdr->overflow) return;
@@ -530,9 +549,9 @@ int launch_sort_pack_t(const RasterLayout& L, cudaStream_t s) {
     // streams join the capture through the events), so the few CTAs of the heavy tiers (one 10^4-key tile takes a
     // 1024-thread CTA ~0.1 ms) run under the bulk of the small tiles instead of in front of them.
     // one set of side streams / events per device (one process per GPU is the design, but a process may own several)
-    constexpr int MAX_DEV = 16;
-    static cudaStream_t side_all[MAX_DEV][3] = {};
-    static cudaEvent_t fork_all[MAX_DEV] = {}, join_all[MAX_DEV][3] = {};
+    constexpr int MAX_DEV = 16, NSIDE = 3 + DM4D_SORT_TIER256 + DM4D_SORT_TIER64;
+    static cudaStream_t side_all[MAX_DEV][NSIDE] = {};
+    static cudaEvent_t fork_all[MAX_DEV] = {}, join_all[MAX_DEV][NSIDE] = {};
     int dev = 0;
     DM4D_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= MAX_DEV) { dm4d_set_error("sort_pack: device ordinal %d out of range", dev); return DM4D_EINVAL; }
@@ -540,19 +559,29 @@ int launch_sort_pack_t(const RasterLayout& L, cudaStream_t s) {
     cudaEvent_t& fork_ev = fork_all[dev];
     cudaEvent_t* join_ev = join_all[dev];
     if (!fork_ev) {
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < NSIDE; ++i) {
             DM4D_CUDA_CHECK(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
             DM4D_CUDA_CHECK(cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming));
         }
         DM4D_CUDA_CHECK(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
     }
     DM4D_CUDA_CHECK(cudaEventRecord(fork_ev, s));
-    for (int i = 0; i < 3; ++i) DM4D_CUDA_CHECK(cudaStreamWaitEvent(side[i], fork_ev, 0));
+    for (int i = 0; i < NSIDE; ++i) DM4D_CUDA_CHECK(cudaStreamWaitEvent(side[i], fork_ev, 0));
+    constexpr int K_H = 256 * 8, K_T = 64 * 8;
     sort_pack_kernel<1024, 16, R4><<<grid(1), 1024, K_X * 8, side[0]>>>(L, K_L, 0x7fffffff);
     sort_pack_kernel<1024, 8, R4><<<grid(1), 1024, K_L * 8, side[1]>>>(L, K_M, K_L);
-    sort_pack_kernel<512, 8, R4><<<grid(4), 512, K_M * 8, side[2]>>>(L, K_S, K_M);
+    sort_pack_kernel<512, 8, R4><<<grid(4), 512, K_M * 8, side[2]>>>(L, DM4D_SORT_TIER256 ? K_H : K_S, K_M);
+#if DM4D_SORT_TIER256
+    sort_pack_kernel<256, 8, R4><<<grid(8), 256, K_H * 8, side[3]>>>(L, K_S, K_H);
+#endif
+#if DM4D_SORT_TIER64
+    // tile_order is heaviest first: the light tier's CTAs skip the head of the list with a few loads per tile
+    sort_pack_kernel<64, 8, R4><<<grid(32), 64, K_T * 8, side[NSIDE - 1]>>>(L, 0, K_T);
+    sort_pack_kernel<128, 8, R4><<<(unsigned)n_all, 128, K_S * 8, s>>>(L, K_T, K_S);
+#else
     sort_pack_kernel<128, 8, R4><<<(unsigned)n_all, 128, K_S * 8, s>>>(L, 0, K_S);
-    for (int i = 0; i < 3; ++i) {
+#endif
+    for (int i = 0; i < NSIDE; ++i) {
         DM4D_CUDA_CHECK(cudaEventRecord(join_ev[i], side[i]));
         DM4D_CUDA_CHECK(cudaStreamWaitEvent(s, join_ev[i], 0));
     }

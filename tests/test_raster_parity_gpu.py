@@ -255,7 +255,7 @@ def test_dropin_shs_path_equals_precomputed_colours():
         assert shs.grad is not None and float(shs.grad.abs().max()) > 0
 
 
-@pytest.mark.parametrize("P", [1023, 1024, 1025, 4096, 4097, 8192, 8193, 16384, 16385, 21000])
+@pytest.mark.parametrize("P", [511, 512, 513, 1023, 1024, 1025, 2048, 2049, 4096, 4097, 8192, 8193, 16384, 16385, 21000])
 def test_tile_sort_tier_boundaries(P):
     """One 16x16 image = one tile holding every Gaussian: segment lengths on both sides of every tier of the per-tile
     sort (128x8, 512x8, 1024x8, 1024x16 keys in shared memory, chunked merging through global memory above 16384).
