@@ -673,8 +673,8 @@ def run_ours(args):
     prof = _lib.profile_collect()
     _lib.profile_enable(False)
     launches_per_step = int(sum(n for _, n in prof.values())) // prof_steps
-    # the tile sort is one profiling scope but two kernel launches (512- and 128-thread CTAs)
-    launches_per_step += int(prof.get("sort_pack_kernel", (0.0, 0))[1]) // prof_steps
+    # the tile sort is one profiling scope but five kernel launches (one per tier: 1024x16, 1024x8, 512x8, 256x8, 128x8 keys)
+    launches_per_step += 4 * (int(prof.get("sort_pack_kernel", (0.0, 0))[1]) // prof_steps)
     if args.kernels_only:
         sampler.result()
         if rank == 0:
