@@ -253,6 +253,10 @@ __global__ void __launch_bounds__(VW == 8 ? 512 : 1024) gn_stream_apply_kernel(N
 // Forward of SMALL activations (the UNet's: at most a few MB, one CTA per (sample, slab) with every CTA resident at once):
 // the slab stays in registers between the statistics and the apply phase — x is read once, and the whole norm is one
 // launch whose critical path is load -> group atomics -> per-sample arrival counter -> store.  fp16 only.
+// Forward progress: a CTA spins on its sample's counter, so every CTA of the launch must eventually be resident — the
+// launcher only takes this path when N x slabs <= SMs x occupancy.  Kernels of OTHER streams merely delay that (they
+// drain); two of THESE launches running concurrently on one device could starve each other, so callers keep the norms of
+// one device on one stream (the Zero123 networks and the step graph do).
 constexpr int RES_IT = 12;                 // pixels per thread kept in registers (packed fp16: 2 registers each)
 
 __global__ void __launch_bounds__(1024, 1) gn_resident_kernel(FusedArgs f, const __half* __restrict__ x, const float* __restrict__ chan_bias,

@@ -545,7 +545,7 @@ int launch_sort_pack_t(const RasterLayout& L, cudaStream_t s) {
     }
     const int n_all = L.n_views * L.tiles;
     auto grid = [&](int per_sm) { return (unsigned)std::max(1, std::min(n_all, 148 * per_sm)); };
-    // The four tiers are independent: fork them onto side streams (works inside a stream capture too — the side
+    // The tiers are independent: fork them onto side streams (works inside a stream capture too — the side
     // streams join the capture through the events), so the few CTAs of the heavy tiers (one 10^4-key tile takes a
     // 1024-thread CTA ~0.1 ms) run under the bulk of the small tiles instead of in front of them.
     // one set of side streams / events per device (one process per GPU is the design, but a process may own several)
